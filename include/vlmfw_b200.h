@@ -1,0 +1,190 @@
+/*
+ * vlmfw_b200 — C ABI of the B200-native vision-tower + probe hot path.
+ *
+ * This is the drop-in boundary for ONE path of andrealb022/Vision-Language-Model-Framework:
+ *   VisionBackbone.forward(images) -> [B, D]          (reference models/vision_backbone.py:28-38)
+ *     PaliGemmaBackbone.forward  (SigLIP-So400m)      (reference models/paligemma.py:100-112)
+ *     LLaVABackbone.forward      (CLIP ViT-L/14-336)  (reference models/llava.py:101-119)
+ *     BLIP2Backbone.forward      (EVA ViT-g/14)       (reference models/blip2.py:83-95)
+ *   probe heads make_head / make_head_deeper          (reference probing/models/base_probe.py:7-22)
+ *   LinearProbe / MultiTaskProbe forward + predict    (reference probing/models/linear_probe.py:35-45,
+ *                                                      probing/models/multitask_probe.py:35-45)
+ *   probe train step on cached features               (reference probing/train/singletask_trainer.py:183-191,
+ *                                                      probing/train/base_trainer.py:166-181)
+ * The tower arithmetic the reference delegates to Hugging Face transformers (modeling_siglip.py,
+ * modeling_clip.py, modeling_blip_2.py) is implemented here as hand-written sm_100a kernels.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative VLMFW_E_* code; nothing throws or aborts across the ABI;
+ *     vlmfw_last_error() returns a thread-local message for the last failure.
+ *   - all pointers are DEVICE pointers owned by the caller unless the name says `host`.
+ *   - `stream` is a cudaStream_t passed as void*; work is asynchronous on it.
+ *   - a tower handle owns its packed weights; it is not thread-safe.
+ *   - there is no CPU fallback: without a sm_100 device every compute entry point fails with VLMFW_E_NODEVICE.
+ */
+#ifndef VLMFW_B200_H
+#define VLMFW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLMFW_ABI_VERSION 1
+
+enum {
+    VLMFW_OK = 0,
+    VLMFW_E_INVALID = -1,   /* bad argument / shape */
+    VLMFW_E_NODEVICE = -2,  /* no CUDA device or not sm_100 */
+    VLMFW_E_CUDA = -3,      /* a CUDA runtime / driver call failed */
+    VLMFW_E_STATE = -4,     /* weights missing, workspace too small, ... */
+    VLMFW_E_NOTFOUND = -5   /* unknown weight name */
+};
+
+/* tower family: which HF vision transformer the adapter wrapped */
+enum { VLMFW_ARCH_SIGLIP = 0, VLMFW_ARCH_CLIP = 1, VLMFW_ARCH_EVA = 2 };
+/* MLP activation (transformers/activations.py): gelu_pytorch_tanh, quick_gelu, gelu (erf) */
+enum { VLMFW_ACT_GELU_TANH = 0, VLMFW_ACT_QUICK_GELU = 1, VLMFW_ACT_GELU_ERF = 2, VLMFW_ACT_NONE = 3 };
+/* pooling done by the reference adapter after the tower */
+enum {
+    VLMFW_POOL_LN_MEAN = 0, /* post_layernorm on all tokens then mean(dim=1)   (paligemma.py:111-112) */
+    VLMFW_POOL_MEAN = 1,    /* mean(dim=1) over raw last_hidden_state incl CLS (llava.py:116-117)     */
+    VLMFW_POOL_CLS = 2,     /* raw last_hidden_state[:,0]                      (llava.py:114-115)     */
+    VLMFW_POOL_LN_CLS_LN = 3 /* pooler_output = LN(LN(h)[:,0])                 (blip2.py:94-95)        */
+};
+/* pixel input formats */
+enum {
+    VLMFW_PIX_U8_NHWC = 0, /* raw RGB bytes [B,H,W,3]; rescale 1/255 and (x-mean)/std are fused on the GPU */
+    VLMFW_PIX_F32_NCHW = 1 /* HF processor output `pixel_values` [B,3,H,W], already normalised */
+};
+/* GEMM epilogues (kernel-level entry point, used by the parity tests) */
+enum {
+    VLMFW_EPI_BIAS_BF16 = 0,     /* out_bf16 = act(acc + bias)                         */
+    VLMFW_EPI_BIAS_RESID_F32 = 1 /* out_f32  = acc + bias + resid_f32[row % resid_mod] */
+};
+
+typedef struct vlmfw_tower_cfg {
+    int32_t arch;       /* VLMFW_ARCH_*                                   */
+    int32_t image_size; /* 224 / 336                                      */
+    int32_t patch_size; /* 14                                             */
+    int32_t hidden;     /* D                                              */
+    int32_t heads;      /* H (head_dim = D / H, must be 64, 72 or 88)     */
+    int32_t mlp;        /* I                                              */
+    int32_t layers;     /* L                                              */
+    int32_t has_cls;    /* class token prepended (CLIP, EVA)              */
+    int32_t has_pre_ln; /* CLIP pre_layrnorm                              */
+    int32_t conv_bias;  /* patch conv has a bias (not CLIP)               */
+    int32_t act;        /* VLMFW_ACT_*                                    */
+    int32_t pool;       /* VLMFW_POOL_*                                   */
+    float ln_eps;
+    float pix_mean[3]; /* used by VLMFW_PIX_U8_NHWC */
+    float pix_std[3];
+} vlmfw_tower_cfg;
+
+typedef struct vlmfw_tower vlmfw_tower;
+
+/* one probe head: BatchNorm1d(D) -> Dropout -> Linear(D,C)              (base_probe.py:7-12)
+ * deeper:         BatchNorm1d(D) -> Dropout -> Linear(D,Hd) -> GELU(erf) -> Dropout -> Linear(Hd,C)  (:14-22)
+ * all pointers fp32 device memory; hidden == 0 selects the linear head (w2/b2 ignored). */
+typedef struct vlmfw_head {
+    const float* bn_weight; /* [D] */
+    const float* bn_bias;   /* [D] */
+    const float* bn_mean;   /* [D] running_mean */
+    const float* bn_var;    /* [D] running_var  */
+    const float* w1;        /* [C,D] or [Hd,D]  */
+    const float* b1;        /* [C]   or [Hd]    */
+    const float* w2;        /* [C,Hd] (deeper)  */
+    const float* b2;        /* [C]    (deeper)  */
+    int32_t classes;        /* C      */
+    int32_t hidden;         /* Hd or 0 */
+    float bn_eps;           /* 1e-5   */
+    int32_t logit_offset;   /* column of this head's first logit in the packed [B, sum C] output */
+} vlmfw_head;
+
+int vlmfw_abi_version(void);
+const char* vlmfw_last_error(void);
+/* 0 if a sm_100 device is usable, else VLMFW_E_NODEVICE */
+int vlmfw_device_ok(void);
+
+/* ------------------------------------------------------------------ tower */
+int vlmfw_tower_create(const vlmfw_tower_cfg* cfg, vlmfw_tower** out);
+void vlmfw_tower_destroy(vlmfw_tower* t);
+/* Canonical weight names (fp32 device source, any row-major contiguous shape with the stated element count):
+ *   patch.w [D,3,p,p]  patch.b [D]  cls [D]  pos [S,D]  pre_ln.w/.b [D]  post_ln.w/.b [D]
+ *   L<i>.ln1.w/.b  L<i>.qkv.w [3D,D]  L<i>.qkv.b [3D]  L<i>.o.w [D,D]  L<i>.o.b
+ *   L<i>.ln2.w/.b  L<i>.fc1.w [I,D]   L<i>.fc1.b [I]   L<i>.fc2.w [D,I] L<i>.fc2.b [D]
+ * Matrices are repacked to bf16 (patch K padded 588->592); vectors stay fp32. */
+int vlmfw_tower_set_weight(vlmfw_tower* t, const char* name, const float* src, int64_t numel, void* stream);
+/* 0 when every tensor the configuration needs has been set, else VLMFW_E_STATE (message names the first missing) */
+int vlmfw_tower_ready(vlmfw_tower* t);
+size_t vlmfw_tower_workspace_bytes(const vlmfw_tower* t, int32_t batch);
+int32_t vlmfw_tower_tokens(const vlmfw_tower* t); /* S */
+/* pixels -> pooled features [B, D] fp32 (what VisionBackbone.forward returns) */
+int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t pix_fmt, int32_t batch, void* workspace,
+                        size_t workspace_bytes, float* pooled_out, void* stream);
+/* same, but also exposes the final hidden state [B*S, D] fp32 inside the workspace (for parity tests) */
+const float* vlmfw_tower_hidden_ptr(const vlmfw_tower* t, void* workspace);
+/* number of kernels the last forward launched (bench.py's gpu_launches claim) */
+int64_t vlmfw_tower_last_launches(const vlmfw_tower* t);
+/* Host-buffer convenience for non-torch hosts: H2D copy, forward, D2H copy, synchronous.
+ * host_pixels: VLMFW_PIX_U8_NHWC bytes; host_pooled: [B, D] floats. Buffers are owned by the handle. */
+int vlmfw_tower_forward_host(vlmfw_tower* t, const uint8_t* host_pixels, int32_t batch, float* host_pooled);
+
+/* ------------------------------------------------------------------ probe */
+/* pooled [B,D] -> packed logits [B, sum C] (+ per-head argmax [B, n_heads], first-max tie rule of torch.argmax).
+ * `heads` is a HOST array of n_heads descriptors. */
+int vlmfw_probe_forward(const float* pooled, int32_t batch, int32_t dim, const vlmfw_head* heads, int32_t n_heads,
+                        float* logits_out, int32_t logits_ld, int32_t* argmax_out, void* stream);
+
+/* Probe train step on cached features, linear head, split so a data-parallel caller can all-reduce between phases:
+ *  1. bn_stats     : stats[0:D] = sum_b x, stats[D:2D] = sum_b x^2 over the local batch, fp64      (all-reduce SUM)
+ *  2. linear_grads : forward BN(train)+dropout+Linear+weighted CE(ignore_index=-1) and backward.
+ *                    bucket = [dW (C*D) | db (C) | dgamma (D) | dbeta (D) | loss_sum | weight_sum], UNNORMALISED
+ *                    sums over the local batch                                                     (all-reduce SUM)
+ *  3. adamw        : params -= lr * (m_hat / (sqrt(v_hat)+eps) + wd * params) with grad = bucket / weight_sum;
+ *                    also updates BN running stats (momentum 0.1, unbiased var) from the global stats.
+ * `n_global` is the number of rows behind `stats` (global batch). keep_mask: uint8 [B,D] or NULL (no dropout). */
+int vlmfw_probe_bn_stats(const float* x, int32_t batch, int32_t dim, double* stats, void* stream);
+/* scratch: fp32 [batch * (classes + 2)]; logits_out: fp32 [batch, classes] */
+int vlmfw_probe_linear_grads(const float* x, const int64_t* targets, int32_t batch, int32_t dim, int32_t classes,
+                             const double* stats, int32_t n_global, float bn_eps, const float* gamma,
+                             const float* beta, const float* weight, const float* bias, const float* class_weight,
+                             const uint8_t* keep_mask, float dropout_p, float* bucket, float* logits_out,
+                             float* scratch, void* stream);
+int vlmfw_probe_adamw(float* params, float* exp_avg, float* exp_avg_sq, const float* bucket, int64_t numel,
+                      int64_t weight_sum_index, int32_t step, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, void* stream);
+int vlmfw_probe_bn_running_update(float* running_mean, float* running_var, const double* stats, int32_t dim,
+                                  int32_t n_global, float momentum, void* stream);
+
+/* ----------------------------------------------------- kernel-level entry points (parity tests, profiling) */
+/* out = epilogue(A[M,K] (bf16, row stride lda) x W[N,K]^T (bf16, row stride ldw)), fp32 accumulation in TMEM.
+ * Row mapping of the output: out_row = (m / grp) * grp_out + (m % grp) + grp_off  (grp <= 0: out_row = m).
+ * resid row = m % resid_mod (resid_mod <= 0: m). K, lda, ldw multiples of 8; N, ldo multiples of 8.
+ * block_n: N tile of the kernel (128 / 192 / 256), 0 = choose the one that wastes the fewest MMA columns. */
+int vlmfw_gemm_bf16(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t m, int32_t n, int32_t k,
+                    const float* bias, int32_t epi, int32_t act, void* out, int32_t ldo, const float* resid,
+                    int32_t ldr, int32_t resid_mod, int32_t grp, int32_t grp_out, int32_t grp_off, int32_t block_n,
+                    void* stream);
+/* y = LayerNorm(x) * gamma + beta over rows of x [rows, dim] fp32; out bf16 (out_f32 == 0) or fp32 (may alias x) */
+int vlmfw_layernorm(const float* x, int32_t rows, int32_t dim, const float* gamma, const float* beta, float eps,
+                    void* out, int32_t out_f32, void* stream);
+/* softmax(Q K^T / sqrt(dh)) V for every (image, head); qkv bf16 [B*S, 3*D] = [q | k | v], heads contiguous inside
+ * each third; out bf16 [B*S, D]. head_dim in {64, 72, 88} (or any multiple of 8 <= 96). */
+int vlmfw_attention(const void* qkv, int32_t batch, int32_t tokens, int32_t heads, int32_t head_dim, void* out,
+                    void* stream);
+/* patch gather: pixels -> A [B*P, kpad] bf16 with k = c*p*p + ky*p + kx (conv weight flattening), zero padded */
+int vlmfw_im2col(const void* pixels, int32_t pix_fmt, int32_t batch, int32_t image_size, int32_t patch_size,
+                 const float* mean, const float* std, void* out, int32_t kpad, void* stream);
+/* pooling epilogue over the final hidden state h [B*S, D] fp32 */
+int vlmfw_pool(const float* h, int32_t batch, int32_t tokens, int32_t dim, int32_t pool, const float* gamma,
+               const float* beta, float eps, float* pooled_out, void* stream);
+/* dst_bf16[rows, dst_ld] = src_f32[rows, cols] (zero pad cols..dst_ld) */
+int vlmfw_pack_bf16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLMFW_B200_H */

@@ -1,0 +1,164 @@
+"""Kernel-level parity (-m gpu): every sm_100a kernel, called through the C-ABI, against a plain fp32 torch
+restatement of the same op on the same seeded tensors. Tolerances are written next to each check."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from vlmfw_b200 import ops, specs  # noqa: E402
+
+
+def _rand(shape, seed, scale=1.0, device="cuda"):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(device)
+
+
+def _act_ref(x, act):
+    if act == specs.ACT_GELU_TANH:
+        return torch.nn.functional.gelu(x, approximate="tanh")
+    if act == specs.ACT_QUICK_GELU:
+        return x * torch.sigmoid(1.702 * x)
+    if act == specs.ACT_GELU_ERF:
+        return torch.nn.functional.gelu(x)
+    return x
+
+
+# (M, N, K): tile-exact, ragged M, ragged N (4304 = 16*256+208), K % 64 = 16 (4304, 592), tiny
+GEMM_SHAPES = [(256, 256, 128), (128, 128, 64), (384, 1152, 1152), (1000, 3456, 1152), (520, 4304, 1152),
+               (520, 1152, 4304), (777, 1152, 592), (64, 144, 144), (130, 432, 144), (40, 176, 384)]
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+@pytest.mark.parametrize("block_n", [0, 128, 192, 256])
+def test_gemm_bias_bf16(cuda_device, m, n, k, block_n):
+    a = _rand((m, k), 1).to(torch.bfloat16)
+    w = _rand((n, k), 2, 1 / math.sqrt(k)).to(torch.bfloat16)
+    bias = _rand((n,), 3, 0.5)
+    out = ops.gemm_bf16(a, w, bias, block_n=block_n)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    # fp32 accumulate of exact bf16 products; only the final bf16 rounding (rel 2^-8) differs
+    torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+    # and it must be the correctly rounded value almost everywhere
+    assert (out.float() - ref.to(torch.bfloat16).float()).abs().max() <= 0.04
+
+
+@pytest.mark.parametrize("act", [specs.ACT_GELU_TANH, specs.ACT_QUICK_GELU, specs.ACT_GELU_ERF])
+def test_gemm_activation(cuda_device, act):
+    m, n, k = 300, 4304, 1152
+    a = _rand((m, k), 4).to(torch.bfloat16)
+    w = _rand((n, k), 5, 2 / math.sqrt(k)).to(torch.bfloat16)
+    bias = _rand((n,), 6, 0.5)
+    out = ops.gemm_bf16(a, w, bias, act=act)
+    ref = _act_ref(a.float() @ w.float().t() + bias, act)
+    torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("m,n,k", [(384, 1152, 1152), (777, 1152, 4304), (130, 144, 304), (64, 1408, 6144)])
+def test_gemm_residual_f32_inplace(cuda_device, m, n, k):
+    a = _rand((m, k), 7).to(torch.bfloat16)
+    w = _rand((n, k), 8, 1 / math.sqrt(k)).to(torch.bfloat16)
+    bias = _rand((n,), 9, 0.5)
+    h = _rand((m, n), 10)
+    ref = a.float() @ w.float().t() + bias + h
+    out = ops.gemm_bf16(a, w, bias, resid=h, out=h)  # in place, as the tower does for the residual stream
+    assert out.data_ptr() == h.data_ptr()
+    # fp32 end to end: only accumulation-order error
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-4)
+
+
+def test_gemm_patch_embed_row_remap(cuda_device):
+    # rows of image b land at b*S + 1 + p (class-token slot left free), residual = pos[p] broadcast over images
+    b, p, s, n, k = 3, 25, 26, 128, 592
+    a = _rand((b * p, k), 11).to(torch.bfloat16)
+    w = _rand((n, k), 12, 1 / math.sqrt(k)).to(torch.bfloat16)
+    pos = _rand((p, n), 13)
+    out = torch.full((b * s, n), -7.0, device="cuda")
+    ops.gemm_bf16(a, w, None, resid=pos, resid_mod=p, out=out, grp=p, grp_out=s, grp_off=1)
+    ref = (a.float() @ w.float().t()).view(b, p, n) + pos
+    got = out.view(b, s, n)
+    torch.testing.assert_close(got[:, 1:], ref, rtol=1e-4, atol=2e-4)
+    assert (got[:, 0] == -7.0).all()
+
+
+def test_gemm_rejects_bad_arguments(cuda_device):
+    from vlmfw_b200._lib import VlmfwError
+
+    a = torch.zeros(8, 20, dtype=torch.bfloat16, device="cuda")  # K not a multiple of 8
+    w = torch.zeros(8, 20, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(VlmfwError):
+        ops.gemm_bf16(a, w)
+
+
+@pytest.mark.parametrize("rows,dim", [(1, 144), (37, 1152), (4096, 1024), (513, 1408), (9, 176), (5, 128)])
+@pytest.mark.parametrize("out_f32", [False, True])
+def test_layernorm(cuda_device, rows, dim, out_f32):
+    x = _rand((rows, dim), 20, 3.0) + 1.5
+    g = 1 + _rand((dim,), 21, 0.1)
+    b = _rand((dim,), 22, 0.1)
+    out = ops.layernorm(x, g, b, 1e-6, out_f32=out_f32)
+    ref = torch.nn.functional.layer_norm(x, (dim,), g, b, 1e-6)
+    if out_f32:
+        torch.testing.assert_close(out, ref, rtol=1e-5, atol=2e-5)
+    else:
+        torch.testing.assert_close(out.float(), ref, rtol=8e-3, atol=8e-3)  # bf16 output rounding
+
+
+def test_layernorm_inplace_f32(cuda_device):
+    x = _rand((77, 1024), 23, 2.0)
+    g, b = 1 + _rand((1024,), 24, 0.1), _rand((1024,), 25, 0.1)
+    ref = torch.nn.functional.layer_norm(x, (1024,), g, b, 1e-5)
+    ops.layernorm(x, g, b, 1e-5, out_f32=True, out=x)
+    torch.testing.assert_close(x, ref, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("batch,tokens,heads,dh", [(2, 256, 16, 72), (2, 577, 16, 64), (2, 257, 16, 88), (3, 16, 2, 72),
+                                                  (3, 26, 2, 64), (3, 17, 2, 88), (1, 64, 1, 64), (1, 65, 3, 8)])
+def test_attention(cuda_device, batch, tokens, heads, dh):
+    d = heads * dh
+    qkv = _rand((batch * tokens, 3 * d), 30, 1.5).to(torch.bfloat16)
+    out = ops.attention(qkv, batch, tokens, heads, dh)
+    q, k, v = (t.view(batch, tokens, heads, dh).transpose(1, 2) for t in qkv.float().split(d, dim=-1))
+    att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), dim=-1)
+    ref = (att @ v).transpose(1, 2).reshape(batch * tokens, d)
+    # P is rounded to bf16 before P·V and the output is bf16: abs error ~ 2^-8 * |v|
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("fmt", ["u8", "f32"])
+def test_im2col(cuda_device, fmt):
+    b, size, p = 3, 56, 14
+    kreal, kpad = 3 * p * p, 592
+    mean, std = (0.48, 0.45, 0.40), (0.27, 0.26, 0.28)
+    g = torch.Generator().manual_seed(40)
+    u8 = torch.randint(0, 256, (b, size, size, 3), generator=g, dtype=torch.uint8)
+    pv = ((u8.float() / 255.0).permute(0, 3, 1, 2) - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    if fmt == "u8":
+        out = ops.im2col(u8.cuda(), size, p, kpad, mean, std)
+    else:
+        out = ops.im2col(pv.contiguous().cuda(), size, p, kpad)
+    gs = size // p
+    ref = pv.reshape(b, 3, gs, p, gs, p).permute(0, 2, 4, 1, 3, 5).reshape(b * gs * gs, kreal)
+    torch.testing.assert_close(out[:, :kreal].float().cpu(), ref, rtol=8e-3, atol=8e-3)
+    assert (out[:, kreal:] == 0).all()
+
+
+@pytest.mark.parametrize("mode", [specs.POOL_LN_MEAN, specs.POOL_MEAN, specs.POOL_CLS, specs.POOL_LN_CLS_LN])
+@pytest.mark.parametrize("b,s,d", [(3, 256, 1152), (2, 577, 1024), (5, 257, 1408), (2, 17, 176)])
+def test_pool(cuda_device, mode, b, s, d):
+    h = _rand((b, s, d), 50, 2.0) + 0.3
+    g, bt = 1 + _rand((d,), 51, 0.1), _rand((d,), 52, 0.1)
+    out = ops.pool(h, mode, g, bt, 1e-6)
+    ln = lambda t: torch.nn.functional.layer_norm(t, (d,), g, bt, 1e-6)  # noqa: E731
+    ref = {specs.POOL_LN_MEAN: lambda: ln(h).mean(1), specs.POOL_MEAN: lambda: h.mean(1), specs.POOL_CLS: lambda: h[:, 0],
+           specs.POOL_LN_CLS_LN: lambda: ln(ln(h)[:, 0])}[mode]()
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_pack_bf16(cuda_device):
+    x = _rand((37, 588), 60)
+    out = ops.pack_bf16(x, 592)
+    assert torch.equal(out[:, :588], x.to(torch.bfloat16))  # bit-exact RNE
+    assert (out[:, 588:] == 0).all()

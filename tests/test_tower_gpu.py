@@ -1,0 +1,78 @@
+"""End-to-end parity (-m gpu): TowerEngine (CUDA, through the C-ABI) vs the fp32 CPU oracle on seeded synthetic images
+and seeded non-degenerate weights. Tolerances are north_star's: pooled-feature cosine >= 0.999; the logit / argmax
+checks live in test_probe_gpu.py."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import tower_oracle as O  # noqa: E402
+from vlmfw_b200 import specs, weights  # noqa: E402
+from vlmfw_b200.engine import TowerEngine  # noqa: E402
+
+COS_MIN = 0.999  # BASELINE.json north_star
+
+
+def _run(spec, n_img, seed, smooth, fmt):
+    sd = weights.seeded_hf_state_dict(spec, seed)
+    eng = TowerEngine(spec, "cuda:0")
+    eng.load_hf_state_dict(sd)
+    imgs = weights.seeded_images_u8(n_img, spec.image_size, seed, smooth=smooth)
+    pv = O.preprocess_u8(imgs, spec.pix_mean, spec.pix_std)
+    got = eng.forward(imgs.cuda() if fmt == "u8" else pv.contiguous().cuda())
+    torch.cuda.synchronize()
+    hid = eng.hidden_state(n_img).float().cpu()
+    can = weights.hf_to_canonical(spec, sd)
+    ref = O.tower_features(spec, can, pv)
+    ref_hid = O.last_hidden(spec, {k: v.float() for k, v in can.items()}, pv)
+    return got.cpu(), ref, hid, ref_hid, eng
+
+
+@pytest.mark.parametrize("name", ["siglip_tiny", "clip_tiny", "eva_tiny"])
+@pytest.mark.parametrize("fmt", ["u8", "f32"])
+@pytest.mark.parametrize("smooth", [False, True])
+def test_tiny_tower_matches_oracle(cuda_device, name, fmt, smooth):
+    spec = specs.SPECS[name]
+    got, ref, hid, ref_hid, eng = _run(spec, 5, 3, smooth, fmt)
+    assert got.shape == ref.shape == (5, spec.hidden)
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=1)
+    assert cos.min() >= COS_MIN, cos
+    # residual stream itself (stricter than the pooled cosine): relative L2 error per image
+    rel = (hid - ref_hid).flatten(1).norm(dim=1) / ref_hid.flatten(1).norm(dim=1)
+    assert rel.max() < 2e-2, rel
+    assert (got - ref).abs().max() < 5e-2 * max(1.0, ref.abs().max().item())
+    assert eng.last_launches > 0
+
+
+def test_clip_cls_strategy(cuda_device):
+    spec = specs.CLIP_TINY.with_pool(specs.POOL_CLS)
+    got, ref, *_ = _run(spec, 4, 5, False, "u8")
+    assert torch.nn.functional.cosine_similarity(got, ref, dim=1).min() >= COS_MIN
+
+
+def test_ragged_batches_and_determinism(cuda_device):
+    spec = specs.SIGLIP_TINY
+    sd = weights.seeded_hf_state_dict(spec, 1)
+    eng = TowerEngine(spec, "cuda:0")
+    eng.load_hf_state_dict(sd)
+    imgs = weights.seeded_images_u8(9, spec.image_size, 1).cuda()
+    full = eng.forward(imgs).clone()
+    again = eng.forward(imgs).clone()
+    assert torch.equal(full, again)  # bit-identical run to run
+    one = torch.cat([eng.forward(imgs[i:i + 1]).clone() for i in range(9)])
+    assert torch.equal(full, one)  # batch-size independent: images never interact
+    assert eng.forward(imgs[:0]).shape == (0, spec.hidden)
+
+
+def test_missing_weight_is_loud(cuda_device):
+    from vlmfw_b200._lib import VlmfwError
+
+    spec = specs.SIGLIP_TINY
+    eng = TowerEngine(spec, "cuda:0")
+    with pytest.raises(VlmfwError):
+        eng.forward(torch.zeros(1, spec.image_size, spec.image_size, 3, dtype=torch.uint8, device="cuda"))
+
+
+def test_cpu_device_is_refused():
+    with pytest.raises(RuntimeError):
+        TowerEngine(specs.SIGLIP_TINY, "cpu")

@@ -1,0 +1,253 @@
+// Fused multi-head attention for the vision towers: softmax(Q K^T / sqrt(dh)) V, no mask, no dropout (eval).
+// Restates hf integrations/sdpa_attention.py:92 (F.scaled_dot_product_attention) as called from
+// modeling_siglip.py:285-309, modeling_clip.py:310-334 and modeling_blip_2.py:328-351.
+//
+// Layout: qkv bf16 [B*S, 3*D] straight out of the fused QKV GEMM — thirds are q | k | v, head h occupies columns
+// [h*dh, (h+1)*dh) of each third (BLIP-2's packed (which, head, dh) order is the same thing). Output bf16 [B*S, D],
+// head-major columns, which is exactly the A operand of the out-proj GEMM: no permute kernels anywhere.
+//
+// One CTA = 64 query rows of one (image, head); 4 warps x 16 rows. K/V stream through a 2-deep cp.async ring in
+// 64-key tiles; scores live in registers (mma.sync m16n8k16, fp32 accumulate), online softmax in fp32 with
+// exp2 and warp-shuffle quad reductions; P is re-used from registers as the A operand of P·V.
+// head_dim 72 / 88 are zero-padded to 80 / 96 in shared memory only (K of QK^T must be a multiple of 16).
+// S in {256, 257, 577}: the ragged last key tile is zero-filled and masked to -inf.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vlmfw {
+namespace {
+
+constexpr int BQ = 64;
+constexpr int BKV = 64;
+constexpr int ATT_THREADS = 128;
+
+template <int DHP>
+struct AttCfg {
+    static constexpr int PITCH = DHP + 8;  // elements; +16 B keeps ldmatrix rows on distinct banks
+    static constexpr int TILE_ELEMS = 64 * PITCH;
+    static constexpr int SMEM_BYTES = 5 * TILE_ELEMS * 2;  // Q + 2 x (K, V)
+    static constexpr int CHUNKS_PER_ROW = DHP / 8;         // 16-byte chunks
+};
+
+// Copy 64 rows x DHP columns (rows >= rows_valid and columns >= dh zero-filled) of one head slice into smem.
+template <int DHP>
+__device__ __forceinline__ void load_tile(__nv_bfloat16* smem_tile, const __nv_bfloat16* gbase, size_t row_stride,
+                                          int row0, int rows_total, int dh) {
+    using C = AttCfg<DHP>;
+    constexpr int TOTAL = 64 * C::CHUNKS_PER_ROW;
+#pragma unroll
+    for (int i = 0; i < TOTAL / ATT_THREADS; ++i) {
+        const int idx = i * ATT_THREADS + threadIdx.x;
+        const int r = idx / C::CHUNKS_PER_ROW;
+        const int c = idx - r * C::CHUNKS_PER_ROW;
+        const bool ok = (row0 + r < rows_total) && (c * 8 < dh);
+        const __nv_bfloat16* src = ok ? gbase + static_cast<size_t>(row0 + r) * row_stride + c * 8 : gbase;
+        cp_async_16(smem_tile + r * C::PITCH + c * 8, src, ok ? 16u : 0u);
+    }
+}
+
+template <int DHP>
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                __nv_bfloat16* __restrict__ out, int tokens,
+                                                                int heads, int dh, float scale_log2) {
+    using C = AttCfg<DHP>;
+    constexpr int KSTEPS = DHP / 16;  // k-steps of Q K^T
+    constexpr int NT_O = DHP / 8;     // n-tiles of the output accumulator
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(att_smem);
+    __nv_bfloat16* sK = sQ + C::TILE_ELEMS;      // [2][64][PITCH]
+    __nv_bfloat16* sV = sK + 2 * C::TILE_ELEMS;  // [2][64][PITCH]
+
+    const int q0 = blockIdx.x * BQ;
+    const int head = blockIdx.y;
+    const int img = blockIdx.z;
+    const int dmodel = heads * dh;
+    const size_t row_stride = static_cast<size_t>(3) * dmodel;
+    const __nv_bfloat16* qg = qkv + static_cast<size_t>(img) * tokens * row_stride + head * dh;
+    const __nv_bfloat16* kg = qg + dmodel;
+    const __nv_bfloat16* vg = qg + 2 * dmodel;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int nkv = (tokens + BKV - 1) / BKV;
+
+    load_tile<DHP>(sQ, qg, row_stride, q0, tokens, dh);
+    load_tile<DHP>(sK, kg, row_stride, 0, tokens, dh);
+    load_tile<DHP>(sV, vg, row_stride, 0, tokens, dh);
+    cp_async_commit();
+
+    uint32_t qf[KSTEPS][4];
+    float o[NT_O][4];
+#pragma unroll
+    for (int i = 0; i < NT_O; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY};
+    float l_run[2] = {0.f, 0.f};
+
+    for (int j = 0; j < nkv; ++j) {
+        const int buf = j & 1;
+        if (j + 1 < nkv) {
+            load_tile<DHP>(sK + (buf ^ 1) * C::TILE_ELEMS, kg, row_stride, (j + 1) * BKV, tokens, dh);
+            load_tile<DHP>(sV + (buf ^ 1) * C::TILE_ELEMS, vg, row_stride, (j + 1) * BKV, tokens, dh);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (j == 0) {
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+                const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = kk * 16 + (lane >> 4) * 8;
+                ldmatrix_x4(smem_u32(sQ + r * C::PITCH + c), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+            }
+        }
+        const __nv_bfloat16* kb = sK + buf * C::TILE_ELEMS;
+        const __nv_bfloat16* vb = sV + buf * C::TILE_ELEMS;
+
+        // ---- scores: 16 query rows x 64 keys per warp
+        float s[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {  // pairs of 8-key n-tiles
+                uint32_t b0, b1, b2, b3;
+                const int key = np * 16 + (lane & 7) + (lane >> 4) * 8;
+                const int c = kk * 16 + ((lane >> 3) & 1) * 8;
+                ldmatrix_x4(smem_u32(kb + key * C::PITCH + c), b0, b1, b2, b3);
+                mma_bf16_16816(s[2 * np], qf[kk], b0, b1);
+                mma_bf16_16816(s[2 * np + 1], qf[kk], b2, b3);
+            }
+        }
+        // ---- mask the ragged tail, online softmax (rows g and g+8 of this warp's 16)
+        const int key_base = j * BKV;
+        if (key_base + BKV > tokens) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k0 = key_base + i * 8 + 2 * t;
+                if (k0 >= tokens) s[i][0] = s[i][2] = -INFINITY;
+                if (k0 + 1 >= tokens) s[i][1] = s[i][3] = -INFINITY;
+            }
+        }
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            mx[0] = fmaxf(mx[0], fmaxf(s[i][0], s[i][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[i][2], s[i][3]));
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        }
+        float corr[2], mscaled[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float m_new = fmaxf(m_run[r], mx[r]);
+            corr[r] = exp2f((m_run[r] - m_new) * scale_log2);  // first tile: exp2(-inf) = 0
+            m_run[r] = m_new;
+            mscaled[r] = m_new * scale_log2;
+        }
+        float rs[2] = {0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s[i][0] = exp2f(s[i][0] * scale_log2 - mscaled[0]);
+            s[i][1] = exp2f(s[i][1] * scale_log2 - mscaled[0]);
+            s[i][2] = exp2f(s[i][2] * scale_log2 - mscaled[1]);
+            s[i][3] = exp2f(s[i][3] * scale_log2 - mscaled[1]);
+            rs[0] += s[i][0] + s[i][1];
+            rs[1] += s[i][2] + s[i][3];
+        }
+        l_run[0] = l_run[0] * corr[0] + rs[0];
+        l_run[1] = l_run[1] * corr[1] + rs[1];
+#pragma unroll
+        for (int i = 0; i < NT_O; ++i) {
+            o[i][0] *= corr[0];
+            o[i][1] *= corr[0];
+            o[i][2] *= corr[1];
+            o[i][3] *= corr[1];
+        }
+        // ---- O += P V  (P straight from the score registers)
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+            uint32_t pa[4];
+            pa[0] = pack_bf16x2(s[2 * ks][0], s[2 * ks][1]);
+            pa[1] = pack_bf16x2(s[2 * ks][2], s[2 * ks][3]);
+            pa[2] = pack_bf16x2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+            pa[3] = pack_bf16x2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+            for (int np = 0; np < NT_O / 2; ++np) {
+                uint32_t b0, b1, b2, b3;
+                const int key = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = np * 16 + (lane >> 4) * 8;
+                ldmatrix_x4_trans(smem_u32(vb + key * C::PITCH + c), b0, b1, b2, b3);
+                mma_bf16_16816(o[2 * np], pa, b0, b1);
+                mma_bf16_16816(o[2 * np + 1], pa, b2, b3);
+            }
+        }
+        __syncthreads();  // everyone is done with `buf` before the next prefetch overwrites buf^1's partner
+    }
+
+    // ---- normalise, stage through smem (Q tile is dead), coalesced 16-byte stores
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+    {
+        const int r0 = warp * 16 + g;
+#pragma unroll
+        for (int i = 0; i < NT_O; ++i) {
+            const int c = i * 8 + 2 * t;
+            *reinterpret_cast<uint32_t*>(sQ + r0 * C::PITCH + c) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
+            *reinterpret_cast<uint32_t*>(sQ + (r0 + 8) * C::PITCH + c) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+        }
+    }
+    __syncthreads();
+    __nv_bfloat16* og = out + static_cast<size_t>(img) * tokens * dmodel + head * dh;
+    const int chunks = dh >> 3;
+    for (int idx = threadIdx.x; idx < BQ * chunks; idx += ATT_THREADS) {
+        const int r = idx / chunks, c = idx - r * chunks;
+        if (q0 + r < tokens) {
+            const uint4 v = *reinterpret_cast<const uint4*>(sQ + r * C::PITCH + c * 8);
+            *reinterpret_cast<uint4*>(og + static_cast<size_t>(q0 + r) * dmodel + c * 8) = v;
+        }
+    }
+}
+
+template <int DHP>
+int launch_att(const void* qkv, int batch, int tokens, int heads, int dh, void* out, cudaStream_t stream) {
+    using C = AttCfg<DHP>;
+    auto kern = attention_kernel<DHP>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VLMFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    dim3 grid((tokens + BQ - 1) / BQ, heads, batch);
+    const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
+    kern<<<grid, ATT_THREADS, C::SMEM_BYTES, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
+                                                       static_cast<__nv_bfloat16*>(out), tokens, heads, dh, scale_log2);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+}  // namespace
+
+int launch_attention(const void* qkv, int batch, int tokens, int heads, int head_dim, void* out, cudaStream_t stream) {
+    VLMFW_REQUIRE(qkv && out, "attention: null pointer");
+    VLMFW_REQUIRE(batch > 0 && tokens > 0 && heads > 0, "attention: bad shape");
+    VLMFW_REQUIRE(head_dim % 8 == 0 && head_dim >= 8 && head_dim <= 96, "attention: head_dim %d unsupported", head_dim);
+    VLMFW_REQUIRE(batch <= 65535 && heads <= 65535, "attention: grid too large");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    if (head_dim <= 64) return launch_att<64>(qkv, batch, tokens, heads, head_dim, out, stream);
+    if (head_dim <= 80) return launch_att<80>(qkv, batch, tokens, heads, head_dim, out, stream);
+    return launch_att<96>(qkv, batch, tokens, heads, head_dim, out, stream);
+}
+
+}  // namespace vlmfw

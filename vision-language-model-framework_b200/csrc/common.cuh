@@ -1,0 +1,74 @@
+// Shared host-side declarations of the kernel launchers (one translation unit per kernel family).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/vlmfw_b200.h"
+
+namespace vlmfw {
+
+// thread-local error message behind vlmfw_last_error()
+void set_error(const char* fmt, ...);
+const char* get_error();
+int64_t& launch_counter();  // counts kernels launched by this library on the calling thread
+
+#define VLMFW_CUDA_OK(expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            ::vlmfw::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                               __LINE__);                                                        \
+            return VLMFW_E_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+#define VLMFW_REQUIRE(cond, ...)          \
+    do {                                  \
+        if (!(cond)) {                    \
+            ::vlmfw::set_error(__VA_ARGS__); \
+            return VLMFW_E_INVALID;       \
+        }                                 \
+    } while (0)
+
+#define VLMFW_LAUNCH_CHECK()                   \
+    do {                                       \
+        ++::vlmfw::launch_counter();           \
+        VLMFW_CUDA_OK(cudaGetLastError());     \
+    } while (0)
+
+struct GemmArgs {
+    const void* a = nullptr;  // [M,K] bf16
+    int lda = 0;
+    const void* w = nullptr;  // [N,K] bf16
+    int ldw = 0;
+    int m = 0, n = 0, k = 0;
+    const float* bias = nullptr;  // [N] or null
+    int epi = VLMFW_EPI_BIAS_BF16;
+    int act = VLMFW_ACT_NONE;
+    void* out = nullptr;
+    int ldo = 0;
+    const float* resid = nullptr;
+    int ldr = 0;
+    int resid_mod = 0;
+    int grp = 0, grp_out = 0, grp_off = 0;
+    int block_n = 0;  // 0 = pick automatically
+};
+
+int device_check();
+int num_sms();
+int launch_gemm(const GemmArgs& g, cudaStream_t stream);
+int launch_layernorm(const float* x, int rows, int dim, const float* gamma, const float* beta, float eps, void* out,
+                     bool out_f32, cudaStream_t stream);
+int launch_attention(const void* qkv, int batch, int tokens, int heads, int head_dim, void* out, cudaStream_t stream);
+int launch_im2col(const void* pixels, int pix_fmt, int batch, int image_size, int patch, const float* mean3,
+                  const float* std3, void* out, int kpad, cudaStream_t stream);
+int launch_fill_cls(const float* cls_pos0, float* h, int batch, int tokens, int dim, cudaStream_t stream);
+int launch_pool(const float* h, int batch, int tokens, int dim, int pool, const float* gamma, const float* beta,
+                float eps, float* pooled, cudaStream_t stream);
+int launch_pack_bf16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, cudaStream_t stream);
+int launch_add_rows(const float* a, const float* b, float* out, int64_t rows, int64_t cols, int64_t a_row0,
+                    cudaStream_t stream);
+
+}  // namespace vlmfw

@@ -1,0 +1,157 @@
+// Patch-embedding front end: pixel gather (conv-as-GEMM operand), class-token rows, weight repacking.
+//
+//   im2col_kernel : hf modeling_siglip.py:124-130,178 / modeling_clip.py:146-158 / modeling_blip_2.py:192-201 —
+//                   Conv2d(3->D, k=p, s=p) is a GEMM over non-overlapping patches: A[b*P + py*G + px, c*p*p + ky*p + kx].
+//                   The image-processor arithmetic (x/255 - mean)/std (hf image_processing_* rescale + normalize) is
+//                   fused here when the input is raw uint8.
+//   fill_cls      : class_embedding + position_embedding[0] written to token 0 of every image
+//                   (modeling_clip.py:208-217, modeling_blip_2.py:247-255)
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vlmfw {
+namespace {
+
+struct PixNorm {
+    float scale[3];  // 1 / (255 * std)
+    float shift[3];  // -mean / std
+};
+
+// One thread produces 8 consecutive k of one patch row (16-byte store).
+template <int PIX_FMT>
+__global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ pixels, int batch, int img, int patch,
+                                                     PixNorm nrm, __nv_bfloat16* __restrict__ out, int kpad) {
+    const int grid_side = img / patch;
+    const int patches = grid_side * grid_side;
+    const int kreal = 3 * patch * patch;
+    const int groups = kpad >> 3;
+    const size_t total = static_cast<size_t>(batch) * patches * groups;
+    for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(idx % groups);
+        const size_t row = idx / groups;
+        const int pidx = static_cast<int>(row % patches);
+        const int b = static_cast<int>(row / patches);
+        const int py = pidx / grid_side, px = pidx % grid_side;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = g * 8 + j;
+            float val = 0.f;
+            if (k < kreal) {
+                const int c = k / (patch * patch);
+                const int rem = k - c * patch * patch;
+                const int ky = rem / patch, kx = rem - ky * patch;
+                const int y = py * patch + ky, x = px * patch + kx;
+                if constexpr (PIX_FMT == VLMFW_PIX_U8_NHWC) {
+                    const uint8_t u =
+                        static_cast<const uint8_t*>(pixels)[((static_cast<size_t>(b) * img + y) * img + x) * 3 + c];
+                    // same op order as the HF processor: rescale (x * 1/255) then normalize ((x - mean) / std)
+                    val = static_cast<float>(u) * nrm.scale[c] + nrm.shift[c];
+                } else {
+                    val = static_cast<const float*>(pixels)[((static_cast<size_t>(b) * 3 + c) * img + y) * img + x];
+                }
+            }
+            f[j] = val;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]);
+        o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]);
+        o.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(out + row * kpad + g * 8) = o;
+    }
+}
+
+__global__ void fill_cls_kernel(const float* __restrict__ cls_pos0, float* __restrict__ h, int batch, int tokens,
+                                int dim) {
+    const int b = blockIdx.x;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x)
+        h[static_cast<size_t>(b) * tokens * dim + d] = cls_pos0[d];
+}
+
+__global__ void pack_bf16_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, __nv_bfloat16* dst,
+                                 int64_t dst_ld) {
+    const int64_t total = rows * dst_ld;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = i / dst_ld, c = i - r * dst_ld;
+        dst[i] = __float2bfloat16_rn(c < cols ? src[r * cols + c] : 0.f);
+    }
+}
+
+// out[r, c] = a[r + a_row0, c] + (b ? b[c] : 0)
+__global__ void add_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                int64_t rows, int64_t cols, int64_t a_row0) {
+    const int64_t total = rows * cols;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        out[i] = a[(r + a_row0) * cols + c] + (b ? b[c] : 0.f);
+    }
+}
+
+int grid_for(size_t total, int threads) {
+    size_t g = (total + threads - 1) / threads;
+    const size_t cap = static_cast<size_t>(num_sms()) * 16;
+    return static_cast<int>(g < cap ? (g == 0 ? 1 : g) : cap);
+}
+
+}  // namespace
+
+int launch_im2col(const void* pixels, int pix_fmt, int batch, int image_size, int patch, const float* mean3,
+                  const float* std3, void* out, int kpad, cudaStream_t stream) {
+    VLMFW_REQUIRE(pixels && out, "im2col: null pointer");
+    VLMFW_REQUIRE(batch > 0 && patch > 0 && image_size % patch == 0, "im2col: image %d not a multiple of patch %d",
+                  image_size, patch);
+    VLMFW_REQUIRE(kpad % 8 == 0 && kpad >= 3 * patch * patch, "im2col: kpad %d too small / unaligned", kpad);
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    PixNorm nrm;
+    for (int c = 0; c < 3; ++c) {
+        const float sd = std3 ? std3[c] : 1.f;
+        const float mu = mean3 ? mean3[c] : 0.f;
+        nrm.scale[c] = 1.0f / (255.0f * sd);
+        nrm.shift[c] = -mu / sd;
+    }
+    const int g = image_size / patch;
+    const size_t total = static_cast<size_t>(batch) * g * g * (kpad / 8);
+    const int threads = 256;
+    if (pix_fmt == VLMFW_PIX_U8_NHWC)
+        im2col_kernel<VLMFW_PIX_U8_NHWC><<<grid_for(total, threads), threads, 0, stream>>>(
+            pixels, batch, image_size, patch, nrm, static_cast<__nv_bfloat16*>(out), kpad);
+    else if (pix_fmt == VLMFW_PIX_F32_NCHW)
+        im2col_kernel<VLMFW_PIX_F32_NCHW><<<grid_for(total, threads), threads, 0, stream>>>(
+            pixels, batch, image_size, patch, nrm, static_cast<__nv_bfloat16*>(out), kpad);
+    else {
+        set_error("im2col: unknown pixel format %d", pix_fmt);
+        return VLMFW_E_INVALID;
+    }
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+int launch_fill_cls(const float* cls_pos0, float* h, int batch, int tokens, int dim, cudaStream_t stream) {
+    fill_cls_kernel<<<batch, 256, 0, stream>>>(cls_pos0, h, batch, tokens, dim);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+int launch_pack_bf16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, cudaStream_t stream) {
+    VLMFW_REQUIRE(src && dst && rows > 0 && cols > 0 && dst_ld >= cols, "pack_bf16: bad arguments");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    pack_bf16_kernel<<<grid_for(static_cast<size_t>(rows * dst_ld), 256), 256, 0, stream>>>(
+        src, rows, cols, static_cast<__nv_bfloat16*>(dst), dst_ld);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+int launch_add_rows(const float* a, const float* b, float* out, int64_t rows, int64_t cols, int64_t a_row0,
+                    cudaStream_t stream) {
+    add_rows_kernel<<<grid_for(static_cast<size_t>(rows * cols), 256), 256, 0, stream>>>(a, b, out, rows, cols, a_row0);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+}  // namespace vlmfw

@@ -1,0 +1,245 @@
+// LayerNorm and the pooling epilogues of the three adapters. All HBM-bound: one pass, 128-bit coalesced accesses,
+// fp32 statistics (two-pass in registers, like torch's native_layer_norm), warp-shuffle reductions.
+//
+//   layernorm_kernel    : hf modeling_siglip.py:348,357 / modeling_clip.py:371,380 (+pre_layrnorm :677) /
+//                         modeling_blip_2.py:389,398 — reads the fp32 residual stream, writes the bf16 GEMM operand
+//   pool_ln_mean_kernel : SigLIP post_layernorm (modeling_siglip.py:618) fused with the adapter's mean(dim=1)
+//                         (reference models/paligemma.py:111-112)
+//   pool_mean_kernel    : LLaVA adapter mean / CLS over the raw last_hidden_state (reference models/llava.py:114-117)
+//   pool_cls_ln2_kernel : BLIP-2 pooler_output = LN(LN(h)[:,0]) (modeling_blip_2.py:523-526, reference blip2.py:94-95)
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vlmfw {
+namespace {
+
+constexpr int LN_MAX_CHUNKS = 12;  // float4 chunks per lane: dim <= 12*32*4 = 1536
+
+// One warp per row. dim % 4 == 0.
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int rows, int dim,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, void* out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int nchunks = dim >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * dim);
+    float4 v[LN_MAX_CHUNKS];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        const int c = i * 32 + lane;
+        if (c < nchunks) {
+            v[i] = xr[c];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(s) / static_cast<float>(dim);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        const int c = i * 32 + lane;
+        if (c < nchunks) {
+            const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (cc * cc + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(dim) + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        const int c = i * 32 + lane;
+        if (c < nchunks) {
+            const float4 g = __ldg(g4 + c);
+            const float4 b = __ldg(b4 + c);
+            float4 y;
+            y.x = (v[i].x - mean) * rstd * g.x + b.x;
+            y.y = (v[i].y - mean) * rstd * g.y + b.y;
+            y.z = (v[i].z - mean) * rstd * g.z + b.z;
+            y.w = (v[i].w - mean) * rstd * g.w + b.w;
+            if constexpr (OUT_F32) {
+                reinterpret_cast<float4*>(static_cast<float*>(out) + static_cast<size_t>(warp) * dim)[c] = y;
+            } else {
+                uint2 o;
+                o.x = pack_bf16x2(y.x, y.y);
+                o.y = pack_bf16x2(y.z, y.w);
+                reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + static_cast<size_t>(warp) * dim)[c] = o;
+            }
+        }
+    }
+}
+
+// SigLIP: pooled[b, d] = mean_s ( (h[b,s,d] - mu_s) * rstd_s ) * gamma[d] + beta[d].
+// grid = (batch, col_slabs). Phase 1: warps compute per-token (mu, rstd) into smem (every slab CTA recomputes them —
+// the second read comes from L2). Phase 2: thread d accumulates its column over the tokens.
+__global__ void __launch_bounds__(256) pool_ln_mean_kernel(const float* __restrict__ h, int tokens, int dim,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps,
+                                                           float* __restrict__ pooled) {
+    extern __shared__ float2 stats[];  // [tokens] (mean, rstd)
+    const int b = blockIdx.x;
+    const float* hb = h + static_cast<size_t>(b) * tokens * dim;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int nchunks = dim >> 2;
+    for (int s = warp; s < tokens; s += nwarps) {
+        const float4* xr = reinterpret_cast<const float4*>(hb + static_cast<size_t>(s) * dim);
+        float4 v[LN_MAX_CHUNKS];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+            const int c = i * 32 + lane;
+            if (c < nchunks) {
+                v[i] = xr[c];
+                sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+        }
+        const float mean = warp_sum(sum) / static_cast<float>(dim);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+            const int c = i * 32 + lane;
+            if (c < nchunks) {
+                const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+                q += (a * a + bb * bb) + (cc * cc + d * d);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(dim) + eps);
+        if (lane == 0) stats[s] = make_float2(mean, rstd);
+    }
+    __syncthreads();
+    const int d = blockIdx.y * blockDim.x + threadIdx.x;
+    if (d < dim) {
+        float acc = 0.f;
+        for (int s = 0; s < tokens; ++s) {
+            const float2 st = stats[s];
+            acc += (hb[static_cast<size_t>(s) * dim + d] - st.x) * st.y;
+        }
+        pooled[static_cast<size_t>(b) * dim + d] = acc / static_cast<float>(tokens) * gamma[d] + beta[d];
+    }
+}
+
+// CLIP adapter: mean over all tokens (first = 0, count = tokens) or the CLS row (count = 1) of the raw hidden state.
+__global__ void __launch_bounds__(256) pool_mean_kernel(const float* __restrict__ h, int tokens, int dim, int count,
+                                                        float* __restrict__ pooled) {
+    const int b = blockIdx.x;
+    const int d = blockIdx.y * blockDim.x + threadIdx.x;
+    if (d >= dim) return;
+    const float* hb = h + static_cast<size_t>(b) * tokens * dim;
+    float acc = 0.f;
+    for (int s = 0; s < count; ++s) acc += hb[static_cast<size_t>(s) * dim + d];
+    pooled[static_cast<size_t>(b) * dim + d] = acc / static_cast<float>(count);
+}
+
+// BLIP-2: y = LN(h[b,0,:]); pooled = LN(y) with the same gamma/beta. One warp per image.
+__global__ void __launch_bounds__(128) pool_cls_ln2_kernel(const float* __restrict__ h, int batch, int tokens, int dim,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps,
+                                                           float* __restrict__ pooled) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= batch) return;
+    const int nchunks = dim >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(h + static_cast<size_t>(b) * tokens * dim);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+    float4 v[LN_MAX_CHUNKS];
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        const int c = i * 32 + lane;
+        if (c < nchunks) v[i] = xr[c];
+    }
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+            const int c = i * 32 + lane;
+            if (c < nchunks) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        const float mean = warp_sum(s) / static_cast<float>(dim);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+            const int c = i * 32 + lane;
+            if (c < nchunks) {
+                const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+                q += (a * a + bb * bb) + (cc * cc + d * d);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(dim) + eps);
+#pragma unroll
+        for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+            const int c = i * 32 + lane;
+            if (c < nchunks) {
+                const float4 g = __ldg(g4 + c);
+                const float4 bt = __ldg(b4 + c);
+                v[i].x = (v[i].x - mean) * rstd * g.x + bt.x;
+                v[i].y = (v[i].y - mean) * rstd * g.y + bt.y;
+                v[i].z = (v[i].z - mean) * rstd * g.z + bt.z;
+                v[i].w = (v[i].w - mean) * rstd * g.w + bt.w;
+            }
+        }
+    }
+    float4* o = reinterpret_cast<float4*>(pooled + static_cast<size_t>(b) * dim);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        const int c = i * 32 + lane;
+        if (c < nchunks) o[c] = v[i];
+    }
+}
+
+}  // namespace
+
+int launch_layernorm(const float* x, int rows, int dim, const float* gamma, const float* beta, float eps, void* out,
+                     bool out_f32, cudaStream_t stream) {
+    VLMFW_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
+    VLMFW_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAX_CHUNKS * 128, "layernorm: bad dim %d", dim);
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    const int warps_per_block = 8;
+    const int grid = (rows + warps_per_block - 1) / warps_per_block;
+    if (out_f32)
+        layernorm_kernel<true><<<grid, warps_per_block * 32, 0, stream>>>(x, rows, dim, gamma, beta, eps, out);
+    else
+        layernorm_kernel<false><<<grid, warps_per_block * 32, 0, stream>>>(x, rows, dim, gamma, beta, eps, out);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+int launch_pool(const float* h, int batch, int tokens, int dim, int pool, const float* gamma, const float* beta,
+                float eps, float* pooled, cudaStream_t stream) {
+    VLMFW_REQUIRE(h && pooled, "pool: null pointer");
+    VLMFW_REQUIRE(batch > 0 && tokens > 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAX_CHUNKS * 128,
+                  "pool: bad shape batch=%d tokens=%d dim=%d", batch, tokens, dim);
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    const int threads = 256;
+    dim3 grid(batch, (dim + threads - 1) / threads);
+    switch (pool) {
+        case VLMFW_POOL_LN_MEAN:
+            VLMFW_REQUIRE(gamma && beta, "pool: LN_MEAN needs gamma/beta");
+            VLMFW_REQUIRE(tokens * sizeof(float2) <= 48 * 1024, "pool: too many tokens %d", tokens);
+            pool_ln_mean_kernel<<<grid, threads, tokens * sizeof(float2), stream>>>(h, tokens, dim, gamma, beta, eps,
+                                                                                     pooled);
+            break;
+        case VLMFW_POOL_MEAN:
+            pool_mean_kernel<<<grid, threads, 0, stream>>>(h, tokens, dim, tokens, pooled);
+            break;
+        case VLMFW_POOL_CLS:
+            pool_mean_kernel<<<grid, threads, 0, stream>>>(h, tokens, dim, 1, pooled);
+            break;
+        case VLMFW_POOL_LN_CLS_LN:
+            VLMFW_REQUIRE(gamma && beta, "pool: LN_CLS_LN needs gamma/beta");
+            pool_cls_ln2_kernel<<<(batch + 3) / 4, 128, 0, stream>>>(h, batch, tokens, dim, gamma, beta, eps, pooled);
+            break;
+        default:
+            set_error("pool: unknown mode %d", pool);
+            return VLMFW_E_INVALID;
+    }
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+}  // namespace vlmfw

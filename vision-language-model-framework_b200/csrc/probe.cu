@@ -1,0 +1,394 @@
+// Probe heads on pooled features: inference epilogue and the data-parallel train step, all fp32.
+//
+//   probe_forward_kernel : reference probing/models/base_probe.py:7-22 (make_head / make_head_deeper) in eval mode,
+//                          every head of a LinearProbe / MultiTaskProbe in ONE launch, plus the argmax that
+//                          LinearProbe.predict / MultiTaskProbe.predict take (linear_probe.py:41-45,
+//                          multitask_probe.py:41-45) — the "parsed attribute" integers of base_tester.py:53-57.
+//   train step kernels   : reference probing/train/singletask_trainer.py:183-191 (head_only(x) -> weighted CE with
+//                          ignore_index=-1, :105-108) + base_trainer.py:166-181 (backward, AdamW step), split into
+//                          phases with plain-sum outputs so that a data-parallel caller can all-reduce them and land
+//                          on exactly the single-process result for the concatenated batch.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vlmfw {
+namespace {
+
+constexpr int MAX_HEADS = 16;
+constexpr int MAX_CLASSES = 32;
+
+struct HeadPack {
+    vlmfw_head h[MAX_HEADS];
+    int n;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// grid = batch, block = 256. smem: xhat[dim] | hid[max_hidden] | lg[MAX_CLASSES]
+__global__ void __launch_bounds__(256) probe_forward_kernel(const float* __restrict__ pooled, int dim, HeadPack hp,
+                                                            int max_hidden, float* __restrict__ logits, int logits_ld,
+                                                            int* __restrict__ argmax_out) {
+    extern __shared__ float psm[];
+    float* xhat = psm;
+    float* hid = psm + dim;
+    float* lg = hid + max_hidden;
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const float* x = pooled + static_cast<size_t>(b) * dim;
+    for (int hi = 0; hi < hp.n; ++hi) {
+        const vlmfw_head& H = hp.h[hi];
+        for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+            // BatchNorm1d eval: (x - running_mean) / sqrt(running_var + eps) * weight + bias
+            xhat[d] = (x[d] - H.bn_mean[d]) * rsqrtf(H.bn_var[d] + H.bn_eps) * H.bn_weight[d] + H.bn_bias[d];
+        }
+        __syncthreads();
+        const float* vec = xhat;
+        int vec_len = dim;
+        const float* wout = H.w1;
+        const float* bout = H.b1;
+        if (H.hidden > 0) {
+            for (int j = warp; j < H.hidden; j += nwarps) {
+                const float* wr = H.w1 + static_cast<size_t>(j) * dim;
+                float acc = 0.f;
+                for (int d = lane; d < dim; d += 32) acc += wr[d] * xhat[d];
+                acc = warp_sum(acc);
+                if (lane == 0) hid[j] = gelu_erf(acc + H.b1[j]);
+            }
+            __syncthreads();
+            vec = hid;
+            vec_len = H.hidden;
+            wout = H.w2;
+            bout = H.b2;
+        }
+        for (int c = warp; c < H.classes; c += nwarps) {
+            const float* wr = wout + static_cast<size_t>(c) * vec_len;
+            float acc = 0.f;
+            for (int d = lane; d < vec_len; d += 32) acc += wr[d] * vec[d];
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                const float v = acc + bout[c];
+                lg[c] = v;
+                logits[static_cast<size_t>(b) * logits_ld + H.logit_offset + c] = v;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && argmax_out != nullptr) {
+            int best = 0;
+            float bv = lg[0];
+            for (int c = 1; c < H.classes; ++c) {
+                if (lg[c] > bv) {  // strict: first maximum wins, like torch.argmax
+                    bv = lg[c];
+                    best = c;
+                }
+            }
+            argmax_out[static_cast<size_t>(b) * hp.n + hi] = best;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ train step
+// stats[d] = sum_b x[b,d], stats[dim+d] = sum_b x[b,d]^2 in fp64 (the variance is a difference of these).
+__global__ void __launch_bounds__(128) bn_stats_kernel(const float* __restrict__ x, int batch, int dim,
+                                                       double* __restrict__ stats) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= dim) return;
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < batch; ++b) {
+        const double v = static_cast<double>(x[static_cast<size_t>(b) * dim + d]);
+        s += v;
+        q += v * v;
+    }
+    stats[d] = s;
+    stats[dim + d] = q;
+}
+
+struct TrainArgs {
+    const float* x;
+    const int64_t* targets;
+    int batch, dim, classes;
+    const double* stats;
+    int n_global;
+    float bn_eps;
+    const float* gamma;
+    const float* beta;
+    const float* weight;
+    const float* bias;
+    const float* class_weight;
+    const uint8_t* keep;
+    float keep_scale;  // 1 / (1 - p)
+    float* bucket;
+    float* logits;
+    float* scratch;  // dlogits [B,C] | loss_b [B] | w_b [B]
+};
+
+__device__ __forceinline__ void bn_mean_rstd(const double* stats, int dim, int d, int n, float eps, float& mean,
+                                             float& rstd) {
+    const double mu = stats[d] / n;
+    double var = stats[dim + d] / n - mu * mu;  // biased variance, as BatchNorm normalises with in train mode
+    if (var < 0.0) var = 0.0;
+    mean = static_cast<float>(mu);
+    rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// Phase A: one block per sample. z = dropout(BN_train(x)); logits = W z + b; softmax-CE with class weights.
+__global__ void __launch_bounds__(256) probe_train_fwd_kernel(TrainArgs a) {
+    extern __shared__ float tsm[];
+    float* z = tsm;           // [dim]
+    float* lg = tsm + a.dim;  // [classes]
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int d = threadIdx.x; d < a.dim; d += blockDim.x) {
+        float mean, rstd;
+        bn_mean_rstd(a.stats, a.dim, d, a.n_global, a.bn_eps, mean, rstd);
+        float y = (a.x[static_cast<size_t>(b) * a.dim + d] - mean) * rstd * a.gamma[d] + a.beta[d];
+        if (a.keep != nullptr) y = a.keep[static_cast<size_t>(b) * a.dim + d] ? y * a.keep_scale : 0.f;
+        z[d] = y;
+    }
+    __syncthreads();
+    for (int c = warp; c < a.classes; c += nwarps) {
+        const float* wr = a.weight + static_cast<size_t>(c) * a.dim;
+        float acc = 0.f;
+        for (int d = lane; d < a.dim; d += 32) acc += wr[d] * z[d];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            lg[c] = acc + a.bias[c];
+            a.logits[static_cast<size_t>(b) * a.classes + c] = lg[c];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float* dl = a.scratch + static_cast<size_t>(b) * a.classes;
+        float* loss_b = a.scratch + static_cast<size_t>(a.batch) * a.classes;
+        float* w_b = loss_b + a.batch;
+        const int64_t y = a.targets[b];
+        if (y < 0 || y >= a.classes) {  // ignore_index = -1: no loss, no gradient
+            for (int c = 0; c < a.classes; ++c) dl[c] = 0.f;
+            loss_b[b] = 0.f;
+            w_b[b] = 0.f;
+        } else {
+            float mx = lg[0];
+            for (int c = 1; c < a.classes; ++c) mx = fmaxf(mx, lg[c]);
+            float se = 0.f;
+            for (int c = 0; c < a.classes; ++c) se += expf(lg[c] - mx);
+            const float lse = mx + logf(se);
+            const float w = a.class_weight ? a.class_weight[y] : 1.f;
+            for (int c = 0; c < a.classes; ++c) dl[c] = w * (expf(lg[c] - lse) - (c == y ? 1.f : 0.f));
+            loss_b[b] = w * (lse - lg[y]);
+            w_b[b] = w;
+        }
+    }
+}
+
+// Phase B: one thread per feature column d, fixed-order loop over the batch (deterministic sums).
+// bucket = [dW (C*D) | db (C) | dgamma (D) | dbeta (D) | loss_sum | weight_sum]
+__global__ void __launch_bounds__(128) probe_train_bwd_kernel(TrainArgs a) {
+    extern __shared__ float bsm[];  // dlogits [B*C]
+    const int nd = a.batch * a.classes;
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) bsm[i] = a.scratch[i];
+    __syncthreads();
+    const int C = a.classes, D = a.dim;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < D) {
+        float mean, rstd;
+        bn_mean_rstd(a.stats, D, d, a.n_global, a.bn_eps, mean, rstd);
+        const float gm = a.gamma[d], bt = a.beta[d];
+        float wcol[MAX_CLASSES];
+        float dw[MAX_CLASSES];
+#pragma unroll
+        for (int c = 0; c < MAX_CLASSES; ++c) {
+            wcol[c] = c < C ? a.weight[static_cast<size_t>(c) * D + d] : 0.f;
+            dw[c] = 0.f;
+        }
+        float dgamma = 0.f, dbeta = 0.f;
+        for (int b = 0; b < a.batch; ++b) {
+            const float xh = (a.x[static_cast<size_t>(b) * D + d] - mean) * rstd;
+            float keep = 1.f;
+            if (a.keep != nullptr) keep = a.keep[static_cast<size_t>(b) * D + d] ? a.keep_scale : 0.f;
+            const float z = (xh * gm + bt) * keep;
+            float dz = 0.f;
+#pragma unroll
+            for (int c = 0; c < MAX_CLASSES; ++c) {
+                if (c < C) {
+                    const float g = bsm[b * C + c];
+                    dw[c] += g * z;
+                    dz += g * wcol[c];
+                }
+            }
+            const float dy = dz * keep;
+            dgamma += dy * xh;
+            dbeta += dy;
+        }
+#pragma unroll
+        for (int c = 0; c < MAX_CLASSES; ++c)
+            if (c < C) a.bucket[static_cast<size_t>(c) * D + d] = dw[c];
+        a.bucket[static_cast<size_t>(C) * D + C + d] = dgamma;
+        a.bucket[static_cast<size_t>(C) * D + C + D + d] = dbeta;
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < C) {
+            float s = 0.f;
+            for (int b = 0; b < a.batch; ++b) s += bsm[b * C + threadIdx.x];
+            a.bucket[static_cast<size_t>(C) * D + threadIdx.x] = s;
+        }
+        if (threadIdx.x == 32) {
+            const float* loss_b = a.scratch + static_cast<size_t>(a.batch) * C;
+            const float* w_b = loss_b + a.batch;
+            float ls = 0.f, ws = 0.f;
+            for (int b = 0; b < a.batch; ++b) {
+                ls += loss_b[b];
+                ws += w_b[b];
+            }
+            a.bucket[static_cast<size_t>(C) * D + C + 2 * D] = ls;
+            a.bucket[static_cast<size_t>(C) * D + C + 2 * D + 1] = ws;
+        }
+    }
+}
+
+// torch.optim.AdamW (decoupled weight decay), grad = bucket[i] / bucket[weight_sum_index]
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                    const float* __restrict__ bucket, int64_t numel,
+                                                    int64_t wsum_index, float lr, float beta1, float beta2, float eps,
+                                                    float wd, float bc1, float bc2_sqrt) {
+    const float wsum = bucket[wsum_index];
+    const float inv = wsum > 0.f ? 1.f / wsum : 0.f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < numel;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float g = bucket[i] * inv;
+        float pi = p[i] * (1.f - lr * wd);
+        const float mi = beta1 * m[i] + (1.f - beta1) * g;
+        const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi -= (lr / bc1) * (mi / denom);
+        p[i] = pi;
+    }
+}
+
+// running_mean/var <- (1-momentum) * old + momentum * batch stat (unbiased variance), nn.BatchNorm1d train mode
+__global__ void bn_running_kernel(float* __restrict__ rm, float* __restrict__ rv, const double* __restrict__ stats,
+                                  int dim, int n, float momentum) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= dim) return;
+    const double mu = stats[d] / n;
+    double var = stats[dim + d] / n - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const double unbiased = n > 1 ? var * n / (n - 1) : var;
+    rm[d] = (1.f - momentum) * rm[d] + momentum * static_cast<float>(mu);
+    rv[d] = (1.f - momentum) * rv[d] + momentum * static_cast<float>(unbiased);
+}
+
+}  // namespace
+}  // namespace vlmfw
+
+using namespace vlmfw;
+
+extern "C" int vlmfw_probe_forward(const float* pooled, int32_t batch, int32_t dim, const vlmfw_head* heads,
+                                   int32_t n_heads, float* logits_out, int32_t logits_ld, int32_t* argmax_out,
+                                   void* stream) {
+    VLMFW_REQUIRE(pooled && heads && logits_out, "probe_forward: null pointer");
+    VLMFW_REQUIRE(batch > 0 && dim > 0, "probe_forward: bad shape");
+    VLMFW_REQUIRE(n_heads > 0 && n_heads <= MAX_HEADS, "probe_forward: 1..%d heads supported", MAX_HEADS);
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    HeadPack hp;
+    hp.n = n_heads;
+    int max_hidden = 0, total = 0;
+    for (int i = 0; i < n_heads; ++i) {
+        hp.h[i] = heads[i];
+        VLMFW_REQUIRE(heads[i].classes > 0 && heads[i].classes <= MAX_CLASSES, "probe_forward: head %d has %d classes",
+                      i, heads[i].classes);
+        VLMFW_REQUIRE(heads[i].bn_weight && heads[i].bn_bias && heads[i].bn_mean && heads[i].bn_var && heads[i].w1 &&
+                          heads[i].b1,
+                      "probe_forward: head %d has null parameters", i);
+        if (heads[i].hidden > 0) VLMFW_REQUIRE(heads[i].w2 && heads[i].b2, "probe_forward: deeper head %d lacks w2/b2", i);
+        max_hidden = heads[i].hidden > max_hidden ? heads[i].hidden : max_hidden;
+        total = heads[i].logit_offset + heads[i].classes > total ? heads[i].logit_offset + heads[i].classes : total;
+    }
+    VLMFW_REQUIRE(logits_ld >= total, "probe_forward: logits_ld %d < %d", logits_ld, total);
+    const size_t smem = static_cast<size_t>(dim + max_hidden + MAX_CLASSES) * sizeof(float);
+    VLMFW_REQUIRE(smem <= 48 * 1024, "probe_forward: dim+hidden too large");
+    probe_forward_kernel<<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(pooled, dim, hp, max_hidden,
+                                                                                  logits_out, logits_ld, argmax_out);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+extern "C" int vlmfw_probe_bn_stats(const float* x, int32_t batch, int32_t dim, double* stats, void* stream) {
+    VLMFW_REQUIRE(x && stats && batch > 0 && dim > 0, "probe_bn_stats: bad arguments");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    bn_stats_kernel<<<(dim + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, batch, dim, stats);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+extern "C" int vlmfw_probe_linear_grads(const float* x, const int64_t* targets, int32_t batch, int32_t dim,
+                                        int32_t classes, const double* stats, int32_t n_global, float bn_eps,
+                                        const float* gamma, const float* beta, const float* weight, const float* bias,
+                                        const float* class_weight, const uint8_t* keep_mask, float dropout_p,
+                                        float* bucket, float* logits_out, float* scratch, void* stream) {
+    VLMFW_REQUIRE(x && targets && stats && gamma && beta && weight && bias && bucket && logits_out && scratch,
+                  "probe_linear_grads: null pointer");
+    VLMFW_REQUIRE(batch > 0 && dim > 0 && classes > 0 && classes <= MAX_CLASSES && n_global >= batch,
+                  "probe_linear_grads: bad shape");
+    VLMFW_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "probe_linear_grads: dropout_p out of range");
+    VLMFW_REQUIRE(static_cast<size_t>(batch) * classes * sizeof(float) <= 48 * 1024,
+                  "probe_linear_grads: batch*classes too large for one launch (split the batch)");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    TrainArgs a;
+    a.x = x;
+    a.targets = targets;
+    a.batch = batch;
+    a.dim = dim;
+    a.classes = classes;
+    a.stats = stats;
+    a.n_global = n_global;
+    a.bn_eps = bn_eps;
+    a.gamma = gamma;
+    a.beta = beta;
+    a.weight = weight;
+    a.bias = bias;
+    a.class_weight = class_weight;
+    a.keep = keep_mask;
+    a.keep_scale = 1.f / (1.f - dropout_p);
+    a.bucket = bucket;
+    a.logits = logits_out;
+    a.scratch = scratch;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    probe_train_fwd_kernel<<<batch, 256, static_cast<size_t>(dim + classes) * sizeof(float), s>>>(a);
+    VLMFW_LAUNCH_CHECK();
+    probe_train_bwd_kernel<<<(dim + 127) / 128, 128, static_cast<size_t>(batch) * classes * sizeof(float), s>>>(a);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+extern "C" int vlmfw_probe_adamw(float* params, float* exp_avg, float* exp_avg_sq, const float* bucket, int64_t numel,
+                                 int64_t weight_sum_index, int32_t step, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay, void* stream) {
+    VLMFW_REQUIRE(params && exp_avg && exp_avg_sq && bucket && numel > 0 && step >= 1, "probe_adamw: bad arguments");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+    int grid = static_cast<int>((numel + 255) / 256);
+    if (grid > 1024) grid = 1024;
+    adamw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, exp_avg, exp_avg_sq, bucket, numel,
+                                                                      weight_sum_index, lr, beta1, beta2, eps,
+                                                                      weight_decay, bc1, bc2_sqrt);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+extern "C" int vlmfw_probe_bn_running_update(float* running_mean, float* running_var, const double* stats, int32_t dim,
+                                             int32_t n_global, float momentum, void* stream) {
+    VLMFW_REQUIRE(running_mean && running_var && stats && dim > 0 && n_global > 0, "probe_bn_running_update: bad arguments");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    bn_running_kernel<<<(dim + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(running_mean, running_var, stats,
+                                                                                        dim, n_global, momentum);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}

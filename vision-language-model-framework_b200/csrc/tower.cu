@@ -1,0 +1,521 @@
+// Tower runtime: owns the packed weights of one vision tower and runs its forward as a fixed kernel sequence on the
+// caller's stream. This is the native replacement for `self.vision_model(pixel_values)` + the adapter pooling in
+//   reference models/paligemma.py:108-112, models/llava.py:109-117, models/blip2.py:91-95
+// i.e. hf SiglipVisionTransformer.forward (modeling_siglip.py:604-625), CLIPVisionTransformer.forward
+// (modeling_clip.py:665-692) and Blip2VisionModel.forward (modeling_blip_2.py:499-533).
+//
+// HBM layout per forward (M = B*S tokens), all inside one caller-provided workspace:
+//   h    fp32 [M, D]    residual stream — kept in fp32 end to end (bf16 residuals miss the
+//                       1e-2 logit tolerance); read by LayerNorm, read-modify-written by the out-proj / fc2 epilogues
+//   xn   bf16 [M, D]    LayerNorm output = A operand of the QKV / fc1 GEMMs
+//   qkv  bf16 [M, 3D]   fused projection, consumed in place by the attention kernel (no head permute)
+//   ctx  bf16 [M, D]    attention output = A operand of out-proj
+//   mid  bf16 [M, I]    GELU(fc1) = A operand of fc2; the patch-gather matrix [B*P, 592] aliases it before layer 0
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vlmfw {
+
+namespace {
+thread_local char g_err[512] = "";
+thread_local int64_t g_launches = 0;
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+int64_t& launch_counter() { return g_launches; }
+
+namespace {
+struct DevInfo {
+    int rc = VLMFW_E_NODEVICE;
+    int sms = 0;
+    char msg[256] = "";
+};
+const DevInfo& dev_info() {
+    static DevInfo info = []() {
+        DevInfo d;
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            snprintf(d.msg, sizeof(d.msg), "no CUDA device (%s); vlmfw_b200 has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+            cudaGetLastError();
+            return d;
+        }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+            snprintf(d.msg, sizeof(d.msg), "cudaGetDeviceProperties failed");
+            return d;
+        }
+        if (p.major != 10) {
+            snprintf(d.msg, sizeof(d.msg), "device %s is sm_%d%d; vlmfw_b200 kernels are sm_100a only", p.name, p.major,
+                     p.minor);
+            return d;
+        }
+        d.rc = VLMFW_OK;
+        d.sms = p.multiProcessorCount;
+        return d;
+    }();
+    return info;
+}
+}  // namespace
+
+int device_check() {
+    const DevInfo& d = dev_info();
+    if (d.rc != VLMFW_OK) set_error("%s", d.msg);
+    return d.rc;
+}
+int num_sms() { return dev_info().sms > 0 ? dev_info().sms : 148; }
+
+}  // namespace vlmfw
+
+using namespace vlmfw;
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Slot {
+    void** dst = nullptr;
+    bool matrix = false;  // repack to bf16 [rows, ld]
+    int64_t rows = 0, cols = 0, ld = 0;
+    bool required = true;
+    bool set = false;
+};
+
+struct LayerW {
+    float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
+    float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+    void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+};
+
+}  // namespace
+
+struct vlmfw_tower {
+    vlmfw_tower_cfg cfg{};
+    int P = 0, S = 0, D = 0, H = 0, dh = 0, I = 0, L = 0, kreal = 0, kpad = 0;
+    std::vector<LayerW> layers;
+    void* patch_w = nullptr;  // bf16 [D, kpad]
+    float* patch_b = nullptr;
+    float* cls = nullptr;
+    float* pos = nullptr;  // [S, D]
+    float *pre_w = nullptr, *pre_b = nullptr, *post_w = nullptr, *post_b = nullptr;
+    float* posb = nullptr;      // derived: pos[has_cls:, :] + patch_b   [P, D]
+    float* cls_pos0 = nullptr;  // derived: cls + pos[0]                 [D]
+    bool derived_ok = false;
+    std::unordered_map<std::string, Slot> slots;
+    int64_t last_launches = 0;
+    // host-buffer path
+    cudaStream_t own_stream = nullptr;
+    void* host_pix_dev = nullptr;
+    size_t host_pix_bytes = 0;
+    void* host_ws = nullptr;
+    size_t host_ws_bytes = 0;
+    float* host_pooled_dev = nullptr;
+    size_t host_pooled_bytes = 0;
+
+    void add_slot(const std::string& name, void** dst, bool matrix, int64_t rows, int64_t cols, int64_t ld,
+                  bool required = true) {
+        Slot s;
+        s.dst = dst;
+        s.matrix = matrix;
+        s.rows = rows;
+        s.cols = cols;
+        s.ld = ld;
+        s.required = required;
+        slots.emplace(name, s);
+    }
+    size_t off_h() const { return 0; }
+    size_t M(int B) const { return static_cast<size_t>(B) * S; }
+    size_t off_xn(int B) const { return align_up(M(B) * D * 4, 1024); }
+    size_t off_qkv(int B) const { return off_xn(B) + align_up(M(B) * D * 2, 1024); }
+    size_t off_ctx(int B) const { return off_qkv(B) + align_up(M(B) * 3 * D * 2, 1024); }
+    size_t off_mid(int B) const { return off_ctx(B) + align_up(M(B) * D * 2, 1024); }
+    size_t ws_bytes(int B) const {
+        size_t mid = M(B) * I * 2;
+        size_t pa = static_cast<size_t>(B) * P * kpad * 2;
+        return off_mid(B) + align_up(mid > pa ? mid : pa, 1024);
+    }
+};
+
+extern "C" int vlmfw_abi_version(void) { return VLMFW_ABI_VERSION; }
+extern "C" const char* vlmfw_last_error(void) { return get_error(); }
+extern "C" int vlmfw_device_ok(void) { return device_check(); }
+
+extern "C" int vlmfw_tower_create(const vlmfw_tower_cfg* cfg, vlmfw_tower** out) {
+    VLMFW_REQUIRE(cfg && out, "tower_create: null argument");
+    VLMFW_REQUIRE(cfg->arch >= VLMFW_ARCH_SIGLIP && cfg->arch <= VLMFW_ARCH_EVA, "tower_create: unknown arch %d", cfg->arch);
+    VLMFW_REQUIRE(cfg->patch_size > 0 && cfg->image_size > 0 && cfg->image_size % cfg->patch_size == 0,
+                  "tower_create: image_size %d must be a multiple of patch_size %d", cfg->image_size, cfg->patch_size);
+    VLMFW_REQUIRE(cfg->hidden > 0 && cfg->heads > 0 && cfg->hidden % cfg->heads == 0, "tower_create: hidden %d / heads %d",
+                  cfg->hidden, cfg->heads);
+    const int dh = cfg->hidden / cfg->heads;
+    VLMFW_REQUIRE(dh % 8 == 0 && dh <= 96, "tower_create: head_dim %d unsupported (multiple of 8, <= 96)", dh);
+    VLMFW_REQUIRE(cfg->hidden % 8 == 0 && cfg->hidden <= 1536, "tower_create: hidden %d unsupported", cfg->hidden);
+    VLMFW_REQUIRE(cfg->mlp > 0 && cfg->mlp % 8 == 0, "tower_create: mlp %d must be a multiple of 8", cfg->mlp);
+    VLMFW_REQUIRE(cfg->layers > 0, "tower_create: layers %d", cfg->layers);
+    VLMFW_REQUIRE(cfg->act >= VLMFW_ACT_GELU_TANH && cfg->act <= VLMFW_ACT_GELU_ERF, "tower_create: act %d", cfg->act);
+    VLMFW_REQUIRE(cfg->pool >= VLMFW_POOL_LN_MEAN && cfg->pool <= VLMFW_POOL_LN_CLS_LN, "tower_create: pool %d", cfg->pool);
+    if (cfg->pool == VLMFW_POOL_CLS || cfg->pool == VLMFW_POOL_LN_CLS_LN)
+        VLMFW_REQUIRE(cfg->has_cls, "tower_create: CLS pooling needs has_cls");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+
+    vlmfw_tower* t = new vlmfw_tower();
+    t->cfg = *cfg;
+    const int g = cfg->image_size / cfg->patch_size;
+    t->P = g * g;
+    t->S = t->P + (cfg->has_cls ? 1 : 0);
+    t->D = cfg->hidden;
+    t->H = cfg->heads;
+    t->dh = dh;
+    t->I = cfg->mlp;
+    t->L = cfg->layers;
+    t->kreal = 3 * cfg->patch_size * cfg->patch_size;
+    t->kpad = static_cast<int>(align_up(t->kreal, 8));
+    t->layers.resize(t->L);
+    const int64_t D = t->D, I = t->I;
+    t->add_slot("patch.w", &t->patch_w, true, D, t->kreal, t->kpad);
+    t->add_slot("patch.b", reinterpret_cast<void**>(&t->patch_b), false, 1, D, D, cfg->conv_bias != 0);
+    t->add_slot("cls", reinterpret_cast<void**>(&t->cls), false, 1, D, D, cfg->has_cls != 0);
+    t->add_slot("pos", reinterpret_cast<void**>(&t->pos), false, t->S, D, D);
+    t->add_slot("pre_ln.w", reinterpret_cast<void**>(&t->pre_w), false, 1, D, D, cfg->has_pre_ln != 0);
+    t->add_slot("pre_ln.b", reinterpret_cast<void**>(&t->pre_b), false, 1, D, D, cfg->has_pre_ln != 0);
+    const bool need_post = cfg->pool == VLMFW_POOL_LN_MEAN || cfg->pool == VLMFW_POOL_LN_CLS_LN;
+    t->add_slot("post_ln.w", reinterpret_cast<void**>(&t->post_w), false, 1, D, D, need_post);
+    t->add_slot("post_ln.b", reinterpret_cast<void**>(&t->post_b), false, 1, D, D, need_post);
+    for (int i = 0; i < t->L; ++i) {
+        LayerW& w = t->layers[i];
+        const std::string p = "L" + std::to_string(i) + ".";
+        t->add_slot(p + "ln1.w", reinterpret_cast<void**>(&w.ln1w), false, 1, D, D);
+        t->add_slot(p + "ln1.b", reinterpret_cast<void**>(&w.ln1b), false, 1, D, D);
+        t->add_slot(p + "qkv.w", &w.wqkv, true, 3 * D, D, D);
+        t->add_slot(p + "qkv.b", reinterpret_cast<void**>(&w.bqkv), false, 1, 3 * D, 3 * D);
+        t->add_slot(p + "o.w", &w.wo, true, D, D, D);
+        t->add_slot(p + "o.b", reinterpret_cast<void**>(&w.bo), false, 1, D, D);
+        t->add_slot(p + "ln2.w", reinterpret_cast<void**>(&w.ln2w), false, 1, D, D);
+        t->add_slot(p + "ln2.b", reinterpret_cast<void**>(&w.ln2b), false, 1, D, D);
+        t->add_slot(p + "fc1.w", &w.w1, true, I, D, D);
+        t->add_slot(p + "fc1.b", reinterpret_cast<void**>(&w.b1), false, 1, I, I);
+        t->add_slot(p + "fc2.w", &w.w2, true, D, I, I);
+        t->add_slot(p + "fc2.b", reinterpret_cast<void**>(&w.b2), false, 1, D, D);
+    }
+    *out = t;
+    return VLMFW_OK;
+}
+
+extern "C" void vlmfw_tower_destroy(vlmfw_tower* t) {
+    if (!t) return;
+    for (auto& kv : t->slots)
+        if (*kv.second.dst) cudaFree(*kv.second.dst);
+    if (t->posb) cudaFree(t->posb);
+    if (t->cls_pos0) cudaFree(t->cls_pos0);
+    if (t->host_pix_dev) cudaFree(t->host_pix_dev);
+    if (t->host_ws) cudaFree(t->host_ws);
+    if (t->host_pooled_dev) cudaFree(t->host_pooled_dev);
+    if (t->own_stream) cudaStreamDestroy(t->own_stream);
+    delete t;
+}
+
+extern "C" int vlmfw_tower_set_weight(vlmfw_tower* t, const char* name, const float* src, int64_t numel, void* stream) {
+    VLMFW_REQUIRE(t && name && src, "tower_set_weight: null argument");
+    auto it = t->slots.find(name);
+    if (it == t->slots.end()) {
+        set_error("tower_set_weight: unknown weight '%s'", name);
+        return VLMFW_E_NOTFOUND;
+    }
+    Slot& s = it->second;
+    VLMFW_REQUIRE(numel == s.rows * s.cols, "tower_set_weight: '%s' expects %lld elements, got %lld", name,
+                  static_cast<long long>(s.rows * s.cols), static_cast<long long>(numel));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (*s.dst == nullptr) {
+        const size_t bytes = s.matrix ? static_cast<size_t>(s.rows * s.ld) * 2 : static_cast<size_t>(numel) * 4;
+        VLMFW_CUDA_OK(cudaMalloc(s.dst, bytes));
+    }
+    if (s.matrix) {
+        int rc = launch_pack_bf16(src, s.rows, s.cols, *s.dst, s.ld, st);
+        if (rc != VLMFW_OK) return rc;
+    } else {
+        VLMFW_CUDA_OK(cudaMemcpyAsync(*s.dst, src, static_cast<size_t>(numel) * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    s.set = true;
+    t->derived_ok = false;
+    return VLMFW_OK;
+}
+
+extern "C" int vlmfw_tower_ready(vlmfw_tower* t) {
+    VLMFW_REQUIRE(t, "tower_ready: null handle");
+    for (auto& kv : t->slots) {
+        if (kv.second.required && !kv.second.set) {
+            set_error("tower weights incomplete: '%s' has not been set", kv.first.c_str());
+            return VLMFW_E_STATE;
+        }
+    }
+    return VLMFW_OK;
+}
+
+extern "C" size_t vlmfw_tower_workspace_bytes(const vlmfw_tower* t, int32_t batch) {
+    if (!t || batch <= 0) return 0;
+    return t->ws_bytes(batch);
+}
+extern "C" int32_t vlmfw_tower_tokens(const vlmfw_tower* t) { return t ? t->S : 0; }
+extern "C" const float* vlmfw_tower_hidden_ptr(const vlmfw_tower* t, void* workspace) {
+    (void)t;
+    return static_cast<const float*>(workspace);
+}
+extern "C" int64_t vlmfw_tower_last_launches(const vlmfw_tower* t) { return t ? t->last_launches : 0; }
+
+static int build_derived(vlmfw_tower* t, cudaStream_t st) {
+    if (t->derived_ok) return VLMFW_OK;
+    if (!t->posb) VLMFW_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&t->posb), static_cast<size_t>(t->P) * t->D * 4));
+    int rc = launch_add_rows(t->pos, t->cfg.conv_bias ? t->patch_b : nullptr, t->posb, t->P, t->D, t->cfg.has_cls ? 1 : 0, st);
+    if (rc != VLMFW_OK) return rc;
+    if (t->cfg.has_cls) {
+        if (!t->cls_pos0) VLMFW_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&t->cls_pos0), static_cast<size_t>(t->D) * 4));
+        rc = launch_add_rows(t->pos, t->cls, t->cls_pos0, 1, t->D, 0, st);
+        if (rc != VLMFW_OK) return rc;
+    }
+    t->derived_ok = true;
+    return VLMFW_OK;
+}
+
+extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t pix_fmt, int32_t batch, void* workspace,
+                                   size_t workspace_bytes, float* pooled_out, void* stream) {
+    VLMFW_REQUIRE(t && pixels && workspace && pooled_out, "tower_forward: null argument");
+    VLMFW_REQUIRE(batch > 0, "tower_forward: batch %d", batch);
+    int rc = vlmfw_tower_ready(t);
+    if (rc != VLMFW_OK) return rc;
+    if (workspace_bytes < t->ws_bytes(batch)) {
+        set_error("tower_forward: workspace %zu bytes < required %zu", workspace_bytes, t->ws_bytes(batch));
+        return VLMFW_E_STATE;
+    }
+    VLMFW_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "tower_forward: workspace must be 1024-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t launches0 = launch_counter();
+    rc = build_derived(t, st);
+    if (rc != VLMFW_OK) return rc;
+
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    float* h = reinterpret_cast<float*>(ws + t->off_h());
+    void* xn = ws + t->off_xn(batch);
+    void* qkv = ws + t->off_qkv(batch);
+    void* ctx = ws + t->off_ctx(batch);
+    void* mid = ws + t->off_mid(batch);
+    void* patch_a = mid;
+    const int D = t->D, I = t->I, S = t->S, P = t->P;
+    const int M = batch * S;
+
+    // ---- embeddings: conv-as-GEMM (+bias +position embedding), class token, optional pre-LN
+    rc = launch_im2col(pixels, pix_fmt, batch, t->cfg.image_size, t->cfg.patch_size, t->cfg.pix_mean, t->cfg.pix_std,
+                       patch_a, t->kpad, st);
+    if (rc != VLMFW_OK) return rc;
+    {
+        GemmArgs g;
+        g.a = patch_a;
+        g.lda = t->kpad;
+        g.w = t->patch_w;
+        g.ldw = t->kpad;
+        g.m = batch * P;
+        g.n = D;
+        g.k = t->kpad;
+        g.epi = VLMFW_EPI_BIAS_RESID_F32;
+        g.out = h;
+        g.ldo = D;
+        g.resid = t->posb;
+        g.ldr = D;
+        g.resid_mod = P;
+        g.grp = P;
+        g.grp_out = S;
+        g.grp_off = t->cfg.has_cls ? 1 : 0;
+        rc = launch_gemm(g, st);
+        if (rc != VLMFW_OK) return rc;
+    }
+    if (t->cfg.has_cls) {
+        rc = launch_fill_cls(t->cls_pos0, h, batch, S, D, st);
+        if (rc != VLMFW_OK) return rc;
+    }
+    if (t->cfg.has_pre_ln) {
+        rc = launch_layernorm(h, M, D, t->pre_w, t->pre_b, t->cfg.ln_eps, h, true, st);
+        if (rc != VLMFW_OK) return rc;
+    }
+    // ---- encoder layers (pre-LN transformer blocks)
+    for (int li = 0; li < t->L; ++li) {
+        const LayerW& w = t->layers[li];
+        rc = launch_layernorm(h, M, D, w.ln1w, w.ln1b, t->cfg.ln_eps, xn, false, st);
+        if (rc != VLMFW_OK) return rc;
+        GemmArgs g;
+        g.a = xn;
+        g.lda = D;
+        g.w = w.wqkv;
+        g.ldw = D;
+        g.m = M;
+        g.n = 3 * D;
+        g.k = D;
+        g.bias = w.bqkv;
+        g.epi = VLMFW_EPI_BIAS_BF16;
+        g.act = VLMFW_ACT_NONE;
+        g.out = qkv;
+        g.ldo = 3 * D;
+        rc = launch_gemm(g, st);
+        if (rc != VLMFW_OK) return rc;
+        rc = launch_attention(qkv, batch, S, t->H, t->dh, ctx, st);
+        if (rc != VLMFW_OK) return rc;
+        g = GemmArgs();
+        g.a = ctx;
+        g.lda = D;
+        g.w = w.wo;
+        g.ldw = D;
+        g.m = M;
+        g.n = D;
+        g.k = D;
+        g.bias = w.bo;
+        g.epi = VLMFW_EPI_BIAS_RESID_F32;
+        g.out = h;
+        g.ldo = D;
+        g.resid = h;
+        g.ldr = D;
+        rc = launch_gemm(g, st);
+        if (rc != VLMFW_OK) return rc;
+        rc = launch_layernorm(h, M, D, w.ln2w, w.ln2b, t->cfg.ln_eps, xn, false, st);
+        if (rc != VLMFW_OK) return rc;
+        g = GemmArgs();
+        g.a = xn;
+        g.lda = D;
+        g.w = w.w1;
+        g.ldw = D;
+        g.m = M;
+        g.n = I;
+        g.k = D;
+        g.bias = w.b1;
+        g.epi = VLMFW_EPI_BIAS_BF16;
+        g.act = t->cfg.act;
+        g.out = mid;
+        g.ldo = I;
+        rc = launch_gemm(g, st);
+        if (rc != VLMFW_OK) return rc;
+        g = GemmArgs();
+        g.a = mid;
+        g.lda = I;
+        g.w = w.w2;
+        g.ldw = I;
+        g.m = M;
+        g.n = D;
+        g.k = I;
+        g.bias = w.b2;
+        g.epi = VLMFW_EPI_BIAS_RESID_F32;
+        g.out = h;
+        g.ldo = D;
+        g.resid = h;
+        g.ldr = D;
+        rc = launch_gemm(g, st);
+        if (rc != VLMFW_OK) return rc;
+    }
+    // ---- adapter pooling -> [B, D] fp32
+    rc = launch_pool(h, batch, S, D, t->cfg.pool, t->post_w, t->post_b, t->cfg.ln_eps, pooled_out, st);
+    if (rc != VLMFW_OK) return rc;
+    t->last_launches = launch_counter() - launches0;
+    return VLMFW_OK;
+}
+
+extern "C" int vlmfw_tower_forward_host(vlmfw_tower* t, const uint8_t* host_pixels, int32_t batch, float* host_pooled) {
+    VLMFW_REQUIRE(t && host_pixels && host_pooled && batch > 0, "tower_forward_host: bad argument");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    if (!t->own_stream) VLMFW_CUDA_OK(cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking));
+    const size_t pix_bytes = static_cast<size_t>(batch) * t->cfg.image_size * t->cfg.image_size * 3;
+    const size_t ws_bytes = t->ws_bytes(batch);
+    const size_t pooled_bytes = static_cast<size_t>(batch) * t->D * 4;
+    if (t->host_pix_bytes < pix_bytes) {
+        if (t->host_pix_dev) cudaFree(t->host_pix_dev);
+        t->host_pix_dev = nullptr;
+        t->host_pix_bytes = 0;
+        VLMFW_CUDA_OK(cudaMalloc(&t->host_pix_dev, pix_bytes));
+        t->host_pix_bytes = pix_bytes;
+    }
+    if (t->host_ws_bytes < ws_bytes) {
+        if (t->host_ws) cudaFree(t->host_ws);
+        t->host_ws = nullptr;
+        t->host_ws_bytes = 0;
+        VLMFW_CUDA_OK(cudaMalloc(&t->host_ws, ws_bytes));
+        t->host_ws_bytes = ws_bytes;
+    }
+    if (t->host_pooled_bytes < pooled_bytes) {
+        if (t->host_pooled_dev) cudaFree(t->host_pooled_dev);
+        t->host_pooled_dev = nullptr;
+        t->host_pooled_bytes = 0;
+        VLMFW_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&t->host_pooled_dev), pooled_bytes));
+        t->host_pooled_bytes = pooled_bytes;
+    }
+    VLMFW_CUDA_OK(cudaMemcpyAsync(t->host_pix_dev, host_pixels, pix_bytes, cudaMemcpyHostToDevice, t->own_stream));
+    rc = vlmfw_tower_forward(t, t->host_pix_dev, VLMFW_PIX_U8_NHWC, batch, t->host_ws, t->host_ws_bytes,
+                             t->host_pooled_dev, t->own_stream);
+    if (rc != VLMFW_OK) return rc;
+    VLMFW_CUDA_OK(cudaMemcpyAsync(host_pooled, t->host_pooled_dev, pooled_bytes, cudaMemcpyDeviceToHost, t->own_stream));
+    VLMFW_CUDA_OK(cudaStreamSynchronize(t->own_stream));
+    return VLMFW_OK;
+}
+
+// ------------------------------------------------------------------------- kernel-level entry points (tests)
+extern "C" int vlmfw_gemm_bf16(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t m, int32_t n, int32_t k,
+                               const float* bias, int32_t epi, int32_t act, void* out, int32_t ldo, const float* resid,
+                               int32_t ldr, int32_t resid_mod, int32_t grp, int32_t grp_out, int32_t grp_off,
+                               int32_t block_n, void* stream) {
+    GemmArgs g;
+    g.a = a;
+    g.lda = lda;
+    g.w = w;
+    g.ldw = ldw;
+    g.m = m;
+    g.n = n;
+    g.k = k;
+    g.bias = bias;
+    g.epi = epi;
+    g.act = act;
+    g.out = out;
+    g.ldo = ldo;
+    g.resid = resid;
+    g.ldr = ldr;
+    g.resid_mod = resid_mod;
+    g.grp = grp;
+    g.grp_out = grp_out;
+    g.grp_off = grp_off;
+    g.block_n = block_n;
+    return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlmfw_layernorm(const float* x, int32_t rows, int32_t dim, const float* gamma, const float* beta,
+                               float eps, void* out, int32_t out_f32, void* stream) {
+    return launch_layernorm(x, rows, dim, gamma, beta, eps, out, out_f32 != 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlmfw_attention(const void* qkv, int32_t batch, int32_t tokens, int32_t heads, int32_t head_dim,
+                               void* out, void* stream) {
+    return launch_attention(qkv, batch, tokens, heads, head_dim, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlmfw_im2col(const void* pixels, int32_t pix_fmt, int32_t batch, int32_t image_size, int32_t patch_size,
+                            const float* mean, const float* std, void* out, int32_t kpad, void* stream) {
+    return launch_im2col(pixels, pix_fmt, batch, image_size, patch_size, mean, std, out, kpad,
+                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlmfw_pool(const float* h, int32_t batch, int32_t tokens, int32_t dim, int32_t pool, const float* gamma,
+                          const float* beta, float eps, float* pooled_out, void* stream) {
+    return launch_pool(h, batch, tokens, dim, pool, gamma, beta, eps, pooled_out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlmfw_pack_bf16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, void* stream) {
+    return launch_pack_bf16(src, rows, cols, dst, dst_ld, static_cast<cudaStream_t>(stream));
+}

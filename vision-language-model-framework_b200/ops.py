@@ -1,0 +1,129 @@
+"""Kernel-level entry points of the C-ABI on torch tensors (used by the parity tests, the profiler and the probes).
+
+Every function launches on the current CUDA stream of the tensor's device and raises ``VlmfwError`` on failure.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from .specs import ACT_NONE
+
+EPI_BIAS_BF16, EPI_BIAS_RESID_F32 = 0, 1
+
+
+def _st(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: vlmfw_b200 has no CPU fallback")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def pack_bf16(src: torch.Tensor, ld: Optional[int] = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 [rows, ld] (zero padded), round-to-nearest-even like torch's ``.to(bfloat16)``."""
+    _need(src, torch.float32, "src")
+    rows, cols = src.shape
+    ld = cols if ld is None else ld
+    dst = torch.empty(rows, ld, dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.load().vlmfw_pack_bf16(src.data_ptr(), rows, cols, dst.data_ptr(), ld, _st(src)))
+    return dst
+
+
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
+              resid: Optional[torch.Tensor] = None, resid_mod: int = 0, out: Optional[torch.Tensor] = None,
+              grp: int = 0, grp_out: int = 0, grp_off: int = 0, out_rows: Optional[int] = None,
+              block_n: int = 0) -> torch.Tensor:
+    """``epilogue(a[M,K] @ w[N,K]^T)`` on tcgen05. Without ``resid``: bf16 ``act(acc + bias)``; with ``resid``
+    (fp32 [*, N]): fp32 ``acc + bias + resid[row % resid_mod]``."""
+    _need(a, torch.bfloat16, "a")
+    _need(w, torch.bfloat16, "w")
+    m, k = a.shape
+    n, k2 = w.shape
+    if k != k2:
+        raise ValueError(f"K mismatch: a {tuple(a.shape)} vs w {tuple(w.shape)}")
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+    rows = m if out_rows is None else out_rows
+    if resid is not None:
+        _need(resid, torch.float32, "resid")
+        epi = EPI_BIAS_RESID_F32
+        if out is None:
+            out = torch.empty(rows, n, dtype=torch.float32, device=a.device)
+        _need(out, torch.float32, "out")
+    else:
+        epi = EPI_BIAS_BF16
+        if out is None:
+            out = torch.empty(rows, n, dtype=torch.bfloat16, device=a.device)
+        _need(out, torch.bfloat16, "out")
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().vlmfw_gemm_bf16(
+            a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), m, n, k,
+            None if bias is None else bias.data_ptr(), epi, act, out.data_ptr(), out.stride(0),
+            None if resid is None else resid.data_ptr(), 0 if resid is None else resid.stride(0), resid_mod,
+            grp, grp_out, grp_off, block_n, _st(a)))
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_f32: bool = False,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(x, torch.float32, "x")
+    _need(gamma, torch.float32, "gamma")
+    _need(beta, torch.float32, "beta")
+    rows, dim = x.shape
+    if out is None:
+        out = torch.empty(rows, dim, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().vlmfw_layernorm(x.data_ptr(), rows, dim, gamma.data_ptr(), beta.data_ptr(), eps,
+                                               out.data_ptr(), int(out_f32), _st(x)))
+    return out
+
+
+def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: int) -> torch.Tensor:
+    """qkv bf16 [B*S, 3*H*dh] (q | k | v thirds) -> softmax(QK^T/sqrt(dh)) V as bf16 [B*S, H*dh]."""
+    _need(qkv, torch.bfloat16, "qkv")
+    d = heads * head_dim
+    if tuple(qkv.shape) != (batch * tokens, 3 * d):
+        raise ValueError(f"qkv must be [{batch * tokens}, {3 * d}], got {tuple(qkv.shape)}")
+    out = torch.empty(batch * tokens, d, dtype=torch.bfloat16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.load().vlmfw_attention(qkv.data_ptr(), batch, tokens, heads, head_dim, out.data_ptr(),
+                                               _st(qkv)))
+    return out
+
+
+def im2col(pixels: torch.Tensor, image_size: int, patch: int, kpad: int, mean: Sequence[float] = (0, 0, 0),
+           std: Sequence[float] = (1, 1, 1)) -> torch.Tensor:
+    if not pixels.is_cuda or not pixels.is_contiguous():
+        raise RuntimeError("pixels must be a contiguous CUDA tensor")
+    fmt = 0 if pixels.dtype == torch.uint8 else 1
+    b = pixels.shape[0]
+    g = image_size // patch
+    out = torch.empty(b * g * g, kpad, dtype=torch.bfloat16, device=pixels.device)
+    m3 = (C.c_float * 3)(*mean)
+    s3 = (C.c_float * 3)(*std)
+    with torch.cuda.device(pixels.device):
+        _lib.check(_lib.load().vlmfw_im2col(pixels.data_ptr(), fmt, b, image_size, patch, m3, s3, out.data_ptr(), kpad,
+                                            _st(pixels)))
+    return out
+
+
+def pool(h: torch.Tensor, mode: int, gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None,
+         eps: float = 1e-6) -> torch.Tensor:
+    """h fp32 [B, S, D] -> pooled fp32 [B, D] (VLMFW_POOL_* mode)."""
+    _need(h, torch.float32, "h")
+    b, s, d = h.shape
+    out = torch.empty(b, d, dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        _lib.check(_lib.load().vlmfw_pool(h.data_ptr(), b, s, d, mode, None if gamma is None else gamma.data_ptr(),
+                                          None if beta is None else beta.data_ptr(), eps, out.data_ptr(), _st(h)))
+    return out
