@@ -1,0 +1,141 @@
+"""CPU: host logic and the C-ABI surface (no compute calls — there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from vlmfw_b200 import _lib, models, parallel, probes, specs, weights
+from vlmfw_b200.vision_backbone import backbone_from_spec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "vlmfw_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vlmfw_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "build the library first (__graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _header_functions()
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/vlmfw_b200.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    assert _lib.load().vlmfw_abi_version() == 1
+
+
+def test_no_device_is_reported_not_faked():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert not _lib.device_ok()
+    assert "no CPU fallback" in _lib.last_error() or "CUDA" in _lib.last_error()
+    cfg = _lib.TowerCfg(arch=0, image_size=56, patch_size=14, hidden=144, heads=2, mlp=304, layers=1, act=0, pool=0)
+    h = ctypes.c_void_p()
+    assert _lib.load().vlmfw_tower_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.E_NODEVICE
+
+
+def test_invalid_config_is_rejected_with_message():
+    cfg = _lib.TowerCfg(arch=7, image_size=56, patch_size=14, hidden=144, heads=2, mlp=304, layers=1)
+    h = ctypes.c_void_p()
+    assert _lib.load().vlmfw_tower_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.E_INVALID
+    assert "arch" in _lib.last_error()
+
+
+@pytest.mark.parametrize("name", ["siglip_tiny", "clip_tiny", "eva_tiny"])
+def test_hf_to_canonical_roundtrip(name):
+    spec = specs.SPECS[name]
+    sd = weights.seeded_hf_state_dict(spec, 0)
+    can = weights.hf_to_canonical(spec, sd)
+    assert sorted(can) == sorted(weights.canonical_names(spec))
+    shapes = weights.canonical_shapes(spec)
+    assert all(tuple(can[k].shape) == shapes[k] for k in can)
+    d = spec.hidden
+    if spec.arch != specs.ARCH_EVA:
+        pre = "vision_model.encoder.layers.1.self_attn."
+        assert torch.equal(can["L1.qkv.w"][d:2 * d], sd[pre + "k_proj.weight"])
+        assert torch.equal(can["L1.qkv.b"][2 * d:], sd[pre + "v_proj.bias"])
+    # checkpoint-style prefixes (probe model.pt: backbone.vision_model.<hf name>) are accepted
+    can2 = weights.hf_to_canonical(spec, {"backbone.vision_model." + k: v for k, v in sd.items()})
+    assert all(torch.equal(can[k], can2[k]) for k in can)
+    bad = dict(sd)
+    bad.pop(next(k for k in bad if "fc1.weight" in k))
+    with pytest.raises(KeyError):
+        weights.hf_to_canonical(spec, bad)
+
+
+def test_seeded_state_dict_matches_hf_module_parameters():
+    from oracle import hf_ref
+
+    for name in ("siglip_tiny", "clip_tiny", "eva_tiny"):
+        spec = specs.SPECS[name]
+        model = hf_ref.build_hf_vision_model(spec, weights.seeded_hf_state_dict(spec, 0))  # strict inside
+        assert {n for n, _ in model.named_parameters()} == {n for n, _ in weights.hf_param_names(spec)}
+
+
+def test_spec_constants_match_survey():
+    assert abs(specs.SIGLIP_SO400M.flops_per_image() / 1e9 - 218.97) < 0.01
+    assert abs(specs.CLIP_VIT_L_336.flops_per_image() / 1e9 - 381.92) < 0.01
+    assert abs(specs.EVA_VIT_G.flops_per_image() / 1e9 - 520.72) < 0.01
+    assert (specs.SIGLIP_SO400M.tokens, specs.CLIP_VIT_L_336.tokens, specs.EVA_VIT_G.tokens) == (256, 577, 257)
+
+
+def test_shard_range_partitions_in_order():
+    for n in (0, 1, 7, 256, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_range(4, 2, 2)
+
+
+def test_factory_surface_is_the_references():
+    f = models.VLMModelFactory
+    assert sorted(f.get_available_models()) == ["blip2", "llava", "paligemma"]
+    with pytest.raises(ValueError, match="non trovato"):
+        f.create_model("nope")
+    assert f._registry["paligemma"].OUTPUT_DIM == 1152 and f._registry["llava"].OUTPUT_DIM == 1024
+    assert f._registry["blip2"].OUTPUT_DIM == 1408
+
+    class FakeRefFactory:
+        _registry = {"blip2": object, "llava": object, "paligemma": object}
+
+    models.install_into_reference(FakeRefFactory)
+    assert FakeRefFactory._registry["llava"] is models.LLaVAModel and set(FakeRefFactory._registry) == {"blip2", "llava", "paligemma"}
+
+
+def test_backbone_and_probe_contract_on_cpu():
+    bb = backbone_from_spec(specs.SIGLIP_TINY, device="cpu")
+    assert bb.output_dim == 144 and isinstance(bb, torch.nn.Module)
+    keys = list(bb.state_dict())
+    assert all(k.startswith("vision_model.") for k in keys)
+    lin = probes.LinearProbe(bb, n_out_classes=9)
+    assert lin._fully_frozen and not any(p.requires_grad for p in bb.parameters())
+    assert {k for k in lin.state_dict() if k.startswith("classifier.")} == {
+        "classifier.0.weight", "classifier.0.bias", "classifier.0.running_mean", "classifier.0.running_var",
+        "classifier.0.num_batches_tracked", "classifier.2.weight", "classifier.2.bias"}
+    deep = probes.LinearProbe(bb, 7, deeper_head=True)
+    assert "classifier.5.weight" in deep.state_dict() and deep.classifier[2].out_features == 512
+    multi = probes.MultiTaskProbe(bb, {"gender": 2, "age": 9})
+    assert "heads.age.2.weight" in multi.state_dict()
+    lin.unfreeze_last_backbone_k_layers(1, parts="attn", include_embeddings=False)
+    assert not lin._fully_frozen
+    names = bb.get_lora_target_names({"last_k": 1, "attn_only": True})
+    assert names and all("encoder.layers.1.self_attn" in n for n in names)
+    # no CPU fallback: the tower path refuses to run off-GPU, loudly
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        bb(torch.zeros(1, 56, 56, 3, dtype=torch.uint8))
+    with pytest.raises(ValueError):
+        backbone_from_spec(specs.CLIP_TINY, device="cpu")(None, strategy="max")
+
+
+def test_parsed_attributes_shape():
+    out = probes.parsed_attributes({"gender": torch.tensor([1, 0]), "hat": torch.tensor([0, 1])})
+    assert out == [{"gender": 1, "hat": 0}, {"gender": 0, "hat": 1}]
+    assert probes.parsed_attributes(torch.tensor([3, 4]), ["age"]) == [{"age": 3}, {"age": 4}]

@@ -1,0 +1,104 @@
+"""Probe heads on the GPU (-m gpu): fused forward + argmax vs the oracle, the native train step vs the reference's
+torch AdamW step, and shard-sum equivalence of the data-parallel phases (ranks emulated on one GPU)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import probe_oracle, tower_oracle as O  # noqa: E402
+from vlmfw_b200 import probes  # noqa: E402
+from vlmfw_b200.probe_train import ProbeTrainStep  # noqa: E402
+
+LOGIT_TOL = 1e-2  # BASELINE.json north_star: probe-logit max abs error
+
+
+def _head(dim, classes, hidden, seed):
+    p = O.seeded_head_params(dim, classes, hidden, seed=seed)
+    m = (probes.make_head_deeper(dim, classes, hidden, 0.3) if hidden else probes.make_head(dim, classes, 0.3))
+    m.load_state_dict(p)
+    return m.cuda().eval(), p
+
+
+@pytest.mark.parametrize("dim", [1152, 1024, 1408, 144])
+@pytest.mark.parametrize("batch", [1, 7, 256])
+def test_fused_heads_forward(cuda_device, dim, batch):
+    feats = torch.randn(batch, dim, generator=torch.Generator().manual_seed(dim + batch))
+    cfgs = [(2, 0), (12, 0), (9, 0), (7, 512), (2, 64)]
+    mods, params = zip(*[_head(dim, c, h, 300 + i) for i, (c, h) in enumerate(cfgs)])
+    logits, amax = probes.fused_heads_forward(feats.cuda(), list(mods))
+    for i, p in enumerate(params):
+        ref = O.head_forward(feats, p)
+        torch.testing.assert_close(logits[i].cpu(), ref, rtol=1e-4, atol=1e-4)  # fp32 both sides
+        assert amax[:, i].cpu().tolist() == ref.argmax(1).tolist()  # bit-exact labels
+
+
+def test_argmax_first_max_tie_rule(cuda_device):
+    m = probes.make_head(8, 4, 0.0)
+    with torch.no_grad():
+        m[2].weight.zero_()
+        m[2].bias.copy_(torch.tensor([1.0, 3.0, 3.0, 2.0]))
+    m = m.cuda().eval()
+    _, amax = probes.fused_heads_forward(torch.randn(5, 8).cuda(), [m])
+    assert amax[:, 0].tolist() == [1] * 5 == torch.tensor([1.0, 3.0, 3.0, 2.0]).argmax().repeat(5).tolist()
+
+
+@pytest.mark.parametrize("dim,classes,n,p", [(1152, 9, 256, 0.3), (144, 5, 33, 0.0), (1024, 2, 64, 0.5)])
+def test_train_steps_match_reference_adamw(cuda_device, dim, classes, n, p):
+    g = torch.Generator().manual_seed(n)
+    state = O.seeded_head_params(dim, classes, 0, seed=9)
+    cw = torch.rand(classes, generator=g) + 0.5
+    batches = []
+    for _ in range(3):
+        x = torch.randn(n, dim, generator=g) * 1.5 + 0.2
+        y = torch.randint(0, classes, (n,), generator=g)
+        y[::9] = -1  # ignore_index rows
+        keep = (torch.rand(n, dim, generator=g) >= p).to(torch.uint8) if p > 0 else None
+        batches.append((x, y, keep))
+    ref_state, ref_losses = probe_oracle.reference_train_steps(state, batches, classes, p, cw, lr=1e-3, weight_decay=1e-2)
+    ts = ProbeTrainStep(dim, classes, "cuda", lr=1e-3, weight_decay=1e-2, dropout_p=p, class_weight=cw)
+    ts.load_head_state_dict({k: v.cuda() for k, v in state.items()})
+    losses = [ts.step(x.cuda(), y.cuda(), keep_mask=None if k is None else k.cuda()) for x, y, k in batches]
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 2e-5 * max(1.0, abs(b))
+    got = ts.head_state_dict()
+    for k in ("2.weight", "2.bias", "0.weight", "0.bias", "0.running_mean", "0.running_var"):
+        torch.testing.assert_close(got[k].cpu(), ref_state[k], rtol=2e-4, atol=2e-6, msg=lambda m, k=k: f"{k}: {m}")
+    assert int(got["0.num_batches_tracked"]) == int(state["0.num_batches_tracked"]) + 3
+
+
+def test_sharded_phases_equal_single_process_gradient(cuda_device):
+    """Config 5's equality check: all-reduced gradient == single-process gradient on the concatenated batch."""
+    dim, classes, n, p = 1152, 9, 256, 0.3
+    g = torch.Generator().manual_seed(1)
+    state = {k: v.cuda() for k, v in O.seeded_head_params(dim, classes, 0, seed=4).items()}
+    x = (torch.randn(n, dim, generator=g) * 1.5).cuda()
+    y = torch.randint(0, classes, (n,), generator=g)
+    y[::11] = -1
+    y = y.cuda()
+    single = ProbeTrainStep(dim, classes, "cuda", dropout_p=p, seed=5)
+    single.load_head_state_dict(state)
+    keep = single.dropout_keep_mask(n, 0, n)
+    single.phase1_stats(x)
+    full_bucket = single.phase2_grads(x, y, n, keep).clone()
+    # emulate 4 ranks: each computes its phases on its slice; sums stand in for the NCCL all-reduce
+    from vlmfw_b200.parallel import shard_range
+
+    ranks = []
+    for r in range(4):
+        t = ProbeTrainStep(dim, classes, "cuda", dropout_p=p, seed=5)
+        t.load_head_state_dict(state)
+        ranks.append(t)
+    spans = [shard_range(n, r, 4) for r in range(4)]
+    stats = sum(t.phase1_stats(x[lo:hi]).clone() for t, (lo, hi) in zip(ranks, spans))
+    torch.testing.assert_close(stats, single.stats, rtol=1e-12, atol=1e-9)
+    total = torch.zeros_like(full_bucket)
+    for t, (lo, hi) in zip(ranks, spans):
+        t.stats.copy_(stats)
+        assert torch.equal(t.dropout_keep_mask(n, lo, hi), keep[lo:hi])  # mask keyed by global row
+        total += t.phase2_grads(x[lo:hi], y[lo:hi], n, keep[lo:hi])
+    torch.testing.assert_close(total, full_bucket, rtol=1e-4, atol=1e-5)
+    # and both agree with the fp64 oracle gradient
+    ref = probe_oracle.phase2_bucket(x.cpu(), y.cpu(), single.stats.cpu(), n, state["0.weight"].cpu(),
+                                     state["0.bias"].cpu(), state["2.weight"].cpu(), state["2.bias"].cpu(), None,
+                                     keep.cpu(), p)
+    torch.testing.assert_close(total.cpu().double(), ref, rtol=1e-3, atol=1e-4)

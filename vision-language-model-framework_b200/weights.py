@@ -14,6 +14,7 @@ Everything here is host logic on CPU tensors and is covered by the ``not gpu`` t
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, Iterable, List, Mapping, Tuple
 
 import torch
@@ -217,3 +218,24 @@ def seeded_images_u8(n: int, size: int, seed: int = 0, smooth: bool = False) -> 
         else:
             imgs.append(torch.from_numpy(rng.integers(0, 256, (size, size, 3), dtype=np.uint8)))
     return torch.stack(imgs)
+
+
+def seeded_head_params(dim: int, classes: int, hidden: int = 0, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded, non-degenerate probe-head parameters in the reference's nn.Sequential keys (``0.*`` BatchNorm1d, ``2.*``
+    Linear, ``5.*`` second Linear of the deeper head). A fresh BatchNorm1d is the identity up to 1/sqrt(1+eps), which
+    would not exercise the affine / running-statistics path."""
+    g = torch.Generator().manual_seed(seed)
+    mid = hidden if hidden > 0 else classes
+    p = {
+        "0.weight": 1.0 + 0.1 * torch.randn(dim, generator=g),
+        "0.bias": 0.1 * torch.randn(dim, generator=g),
+        "0.running_mean": 0.2 * torch.randn(dim, generator=g),
+        "0.running_var": 0.5 + torch.rand(dim, generator=g),
+        "0.num_batches_tracked": torch.tensor(7),
+        "2.weight": torch.randn(mid, dim, generator=g) / math.sqrt(dim),
+        "2.bias": 0.1 * torch.randn(mid, generator=g),
+    }
+    if hidden > 0:
+        p["5.weight"] = torch.randn(classes, hidden, generator=g) / math.sqrt(hidden)
+        p["5.bias"] = 0.1 * torch.randn(classes, generator=g)
+    return p
