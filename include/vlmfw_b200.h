@@ -40,7 +40,8 @@ enum {
     VLMFW_E_NODEVICE = -2,  /* no CUDA device or not sm_100 */
     VLMFW_E_CUDA = -3,      /* a CUDA runtime / driver call failed */
     VLMFW_E_STATE = -4,     /* weights missing, workspace too small, ... */
-    VLMFW_E_NOTFOUND = -5   /* unknown weight name */
+    VLMFW_E_NOTFOUND = -5,  /* unknown weight name */
+    VLMFW_E_RANGE = -6      /* a weight does not fit the fp16 range: recreate the tower with VLMFW_CDT_BF16 */
 };
 
 /* tower family: which HF vision transformer the adapter wrapped */
@@ -59,6 +60,18 @@ enum {
     VLMFW_PIX_U8_NHWC = 0, /* raw RGB bytes [B,H,W,3]; rescale 1/255 and (x-mean)/std are fused on the GPU */
     VLMFW_PIX_F32_NCHW = 1 /* HF processor output `pixel_values` [B,3,H,W], already normalised */
 };
+/* element types of kernel operands / outputs */
+enum { VLMFW_DT_BF16 = 0, VLMFW_DT_F16 = 1, VLMFW_DT_F32 = 2 };
+/* 16-bit format of the tensor-core operands of a tower (weights AND activations: one tcgen05.mma kind::f16 takes A and
+ * B in the same format — mixing raises an illegal-instruction fault on B200). Same tensor pipe, same peak.
+ *   F16  (default): 11-bit mantissa. Weight rounding is the dominant error term of this path because it is coherent
+ *         across tokens and survives mean pooling (DESIGN.md "numerics": bf16 weights alone put the probe-logit error at
+ *         1.5e-2, above the 1e-2 tolerance; fp16 gives 1.2e-3). It is also what the reference itself runs on a GPU
+ *         (fp16 autocast, probing/test/base_tester.py:50). The residual stream, LayerNorm statistics, softmax and all
+ *         accumulation stay fp32; 16-bit stores saturate to +-65504 instead of overflowing to inf.
+ *   BF16: 8-bit mantissa, fp32 range — for checkpoints whose weights exceed the fp16 range (set_weight reports
+ *         VLMFW_E_RANGE and the host recreates the tower with this mode). */
+enum { VLMFW_CDT_F16 = 0, VLMFW_CDT_BF16 = 1 };
 /* GEMM epilogues (kernel-level entry point, used by the parity tests) */
 enum {
     VLMFW_EPI_BIAS_BF16 = 0,     /* out_bf16 = act(acc + bias)                         */
@@ -81,6 +94,7 @@ typedef struct vlmfw_tower_cfg {
     float ln_eps;
     float pix_mean[3]; /* used by VLMFW_PIX_U8_NHWC */
     float pix_std[3];
+    int32_t compute_dtype; /* VLMFW_CDT_* */
 } vlmfw_tower_cfg;
 
 typedef struct vlmfw_tower vlmfw_tower;
@@ -115,7 +129,7 @@ void vlmfw_tower_destroy(vlmfw_tower* t);
  *   patch.w [D,3,p,p]  patch.b [D]  cls [D]  pos [S,D]  pre_ln.w/.b [D]  post_ln.w/.b [D]
  *   L<i>.ln1.w/.b  L<i>.qkv.w [3D,D]  L<i>.qkv.b [3D]  L<i>.o.w [D,D]  L<i>.o.b
  *   L<i>.ln2.w/.b  L<i>.fc1.w [I,D]   L<i>.fc1.b [I]   L<i>.fc2.w [D,I] L<i>.fc2.b [D]
- * Matrices are repacked to bf16 (patch K padded 588->592); vectors stay fp32. */
+ * Matrices are repacked to cfg.compute_dtype (patch K padded 588->592); vectors stay fp32. */
 int vlmfw_tower_set_weight(vlmfw_tower* t, const char* name, const float* src, int64_t numel, void* stream);
 /* 0 when every tensor the configuration needs has been set, else VLMFW_E_STATE (message names the first missing) */
 int vlmfw_tower_ready(vlmfw_tower* t);
@@ -160,29 +174,32 @@ int vlmfw_probe_bn_running_update(float* running_mean, float* running_var, const
                                   int32_t n_global, float momentum, void* stream);
 
 /* ----------------------------------------------------- kernel-level entry points (parity tests, profiling) */
-/* out = epilogue(A[M,K] (bf16, row stride lda) x W[N,K]^T (bf16, row stride ldw)), fp32 accumulation in TMEM.
+/* out = epilogue(A[M,K] x W[N,K]^T), fp32 accumulation in TMEM. A (row stride lda) and W (row stride ldw) are both
+ * `dtype` (VLMFW_DT_BF16 or VLMFW_DT_F16). VLMFW_EPI_BIAS_BF16 writes act(acc + bias) in that same 16-bit dtype;
+ * VLMFW_EPI_BIAS_RESID_F32 writes fp32 acc + bias + resid.
  * Row mapping of the output: out_row = (m / grp) * grp_out + (m % grp) + grp_off  (grp <= 0: out_row = m).
  * resid row = m % resid_mod (resid_mod <= 0: m). K, lda, ldw multiples of 8; N, ldo multiples of 8.
  * block_n: N tile of the kernel (128 / 192 / 256), 0 = choose the one that wastes the fewest MMA columns. */
-int vlmfw_gemm_bf16(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t m, int32_t n, int32_t k,
-                    const float* bias, int32_t epi, int32_t act, void* out, int32_t ldo, const float* resid,
-                    int32_t ldr, int32_t resid_mod, int32_t grp, int32_t grp_out, int32_t grp_off, int32_t block_n,
-                    void* stream);
-/* y = LayerNorm(x) * gamma + beta over rows of x [rows, dim] fp32; out bf16 (out_f32 == 0) or fp32 (may alias x) */
+int vlmfw_gemm_tn(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t dtype, int32_t m, int32_t n,
+                  int32_t k, const float* bias, int32_t epi, int32_t act, void* out, int32_t ldo, const float* resid,
+                  int32_t ldr, int32_t resid_mod, int32_t grp, int32_t grp_out, int32_t grp_off, int32_t block_n,
+                  void* stream);
+/* y = LayerNorm(x) * gamma + beta over rows of x [rows, dim] fp32; out_dtype VLMFW_DT_* (fp32 output may alias x) */
 int vlmfw_layernorm(const float* x, int32_t rows, int32_t dim, const float* gamma, const float* beta, float eps,
-                    void* out, int32_t out_f32, void* stream);
-/* softmax(Q K^T / sqrt(dh)) V for every (image, head); qkv bf16 [B*S, 3*D] = [q | k | v], heads contiguous inside
- * each third; out bf16 [B*S, D]. head_dim in {64, 72, 88} (or any multiple of 8 <= 96). */
-int vlmfw_attention(const void* qkv, int32_t batch, int32_t tokens, int32_t heads, int32_t head_dim, void* out,
-                    void* stream);
-/* patch gather: pixels -> A [B*P, kpad] bf16 with k = c*p*p + ky*p + kx (conv weight flattening), zero padded */
+                    void* out, int32_t out_dtype, void* stream);
+/* softmax(Q K^T / sqrt(dh)) V for every (image, head); qkv 16-bit (`dtype`) [B*S, 3*D] = [q | k | v], heads contiguous
+ * inside each third; out same dtype [B*S, D]. head_dim in {64, 72, 88} (or any multiple of 8 <= 96). */
+int vlmfw_attention(const void* qkv, int32_t dtype, int32_t batch, int32_t tokens, int32_t heads, int32_t head_dim,
+                    void* out, void* stream);
+/* patch gather: pixels -> A [B*P, kpad] (out_dtype VLMFW_DT_*) with k = c*p*p + ky*p + kx (conv weight flattening),
+ * zero padded */
 int vlmfw_im2col(const void* pixels, int32_t pix_fmt, int32_t batch, int32_t image_size, int32_t patch_size,
-                 const float* mean, const float* std, void* out, int32_t kpad, void* stream);
+                 const float* mean, const float* std, void* out, int32_t kpad, int32_t out_dtype, void* stream);
 /* pooling epilogue over the final hidden state h [B*S, D] fp32 */
 int vlmfw_pool(const float* h, int32_t batch, int32_t tokens, int32_t dim, int32_t pool, const float* gamma,
                const float* beta, float eps, float* pooled_out, void* stream);
-/* dst_bf16[rows, dst_ld] = src_f32[rows, cols] (zero pad cols..dst_ld) */
-int vlmfw_pack_bf16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, void* stream);
+/* dst_16[rows, dst_ld] = round_to_nearest_even(src_f32[rows, cols]) as VLMFW_DT_* (zero pad cols..dst_ld) */
+int vlmfw_pack_16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,7 +36,7 @@ def test_gemm_bias_bf16(cuda_device, m, n, k, block_n):
     a = _rand((m, k), 1).to(torch.bfloat16)
     w = _rand((n, k), 2, 1 / math.sqrt(k)).to(torch.bfloat16)
     bias = _rand((n,), 3, 0.5)
-    out = ops.gemm_bf16(a, w, bias, block_n=block_n)
+    out = ops.gemm_tn(a, w, bias, block_n=block_n)
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t() + bias
     # fp32 accumulate of exact bf16 products; only the final bf16 rounding (rel 2^-8) differs
@@ -51,7 +51,7 @@ def test_gemm_activation(cuda_device, act):
     a = _rand((m, k), 4).to(torch.bfloat16)
     w = _rand((n, k), 5, 2 / math.sqrt(k)).to(torch.bfloat16)
     bias = _rand((n,), 6, 0.5)
-    out = ops.gemm_bf16(a, w, bias, act=act)
+    out = ops.gemm_tn(a, w, bias, act=act)
     ref = _act_ref(a.float() @ w.float().t() + bias, act)
     torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
 
@@ -63,7 +63,7 @@ def test_gemm_residual_f32_inplace(cuda_device, m, n, k):
     bias = _rand((n,), 9, 0.5)
     h = _rand((m, n), 10)
     ref = a.float() @ w.float().t() + bias + h
-    out = ops.gemm_bf16(a, w, bias, resid=h, out=h)  # in place, as the tower does for the residual stream
+    out = ops.gemm_tn(a, w, bias, resid=h, out=h)  # in place, as the tower does for the residual stream
     assert out.data_ptr() == h.data_ptr()
     # fp32 end to end: only accumulation-order error
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-4)
@@ -76,7 +76,7 @@ def test_gemm_patch_embed_row_remap(cuda_device):
     w = _rand((n, k), 12, 1 / math.sqrt(k)).to(torch.bfloat16)
     pos = _rand((p, n), 13)
     out = torch.full((b * s, n), -7.0, device="cuda")
-    ops.gemm_bf16(a, w, None, resid=pos, resid_mod=p, out=out, grp=p, grp_out=s, grp_off=1)
+    ops.gemm_tn(a, w, None, resid=pos, resid_mod=p, out=out, grp=p, grp_out=s, grp_off=1)
     ref = (a.float() @ w.float().t()).view(b, p, n) + pos
     got = out.view(b, s, n)
     torch.testing.assert_close(got[:, 1:], ref, rtol=1e-4, atol=2e-4)
@@ -89,46 +89,49 @@ def test_gemm_rejects_bad_arguments(cuda_device):
     a = torch.zeros(8, 20, dtype=torch.bfloat16, device="cuda")  # K not a multiple of 8
     w = torch.zeros(8, 20, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(VlmfwError):
-        ops.gemm_bf16(a, w)
+        ops.gemm_tn(a, w)
 
 
 @pytest.mark.parametrize("rows,dim", [(1, 144), (37, 1152), (4096, 1024), (513, 1408), (9, 176), (5, 128)])
-@pytest.mark.parametrize("out_f32", [False, True])
-def test_layernorm(cuda_device, rows, dim, out_f32):
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_layernorm(cuda_device, rows, dim, dtype):
     x = _rand((rows, dim), 20, 3.0) + 1.5
     g = 1 + _rand((dim,), 21, 0.1)
     b = _rand((dim,), 22, 0.1)
-    out = ops.layernorm(x, g, b, 1e-6, out_f32=out_f32)
+    out = ops.layernorm(x, g, b, 1e-6, dtype=dtype)
+    assert out.dtype == dtype
     ref = torch.nn.functional.layer_norm(x, (dim,), g, b, 1e-6)
-    if out_f32:
-        torch.testing.assert_close(out, ref, rtol=1e-5, atol=2e-5)
-    else:
-        torch.testing.assert_close(out.float(), ref, rtol=8e-3, atol=8e-3)  # bf16 output rounding
+    tol = {torch.float32: 2e-5, torch.float16: 1e-3, torch.bfloat16: 8e-3}[dtype]  # output rounding
+    torch.testing.assert_close(out.float(), ref, rtol=tol, atol=tol)
 
 
 def test_layernorm_inplace_f32(cuda_device):
     x = _rand((77, 1024), 23, 2.0)
     g, b = 1 + _rand((1024,), 24, 0.1), _rand((1024,), 25, 0.1)
     ref = torch.nn.functional.layer_norm(x, (1024,), g, b, 1e-5)
-    ops.layernorm(x, g, b, 1e-5, out_f32=True, out=x)
+    ops.layernorm(x, g, b, 1e-5, out=x)
     torch.testing.assert_close(x, ref, rtol=1e-5, atol=2e-5)
 
 
 @pytest.mark.parametrize("batch,tokens,heads,dh", [(2, 256, 16, 72), (2, 577, 16, 64), (2, 257, 16, 88), (3, 16, 2, 72),
                                                   (3, 26, 2, 64), (3, 17, 2, 88), (1, 64, 1, 64), (1, 65, 3, 8)])
-def test_attention(cuda_device, batch, tokens, heads, dh):
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_attention(cuda_device, batch, tokens, heads, dh, dtype):
     d = heads * dh
-    qkv = _rand((batch * tokens, 3 * d), 30, 1.5).to(torch.bfloat16)
+    qkv = _rand((batch * tokens, 3 * d), 30, 1.5).to(dtype)
     out = ops.attention(qkv, batch, tokens, heads, dh)
     q, k, v = (t.view(batch, tokens, heads, dh).transpose(1, 2) for t in qkv.float().split(d, dim=-1))
     att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), dim=-1)
     ref = (att @ v).transpose(1, 2).reshape(batch * tokens, d)
-    # P is rounded to bf16 before P·V and the output is bf16: abs error ~ 2^-8 * |v|
-    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+    # P is rounded to 16 bits before P·V and the output is 16-bit: abs error ~ 2^-8 (bf16) / 2^-11 (fp16) * |v|
+    tol = 2e-2 if dtype == torch.bfloat16 else 3e-3
+    assert out.dtype == dtype
+    torch.testing.assert_close(out.float(), ref, rtol=tol, atol=tol)
 
 
 @pytest.mark.parametrize("fmt", ["u8", "f32"])
-def test_im2col(cuda_device, fmt):
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_im2col(cuda_device, fmt, dtype):
     b, size, p = 3, 56, 14
     kreal, kpad = 3 * p * p, 592
     mean, std = (0.48, 0.45, 0.40), (0.27, 0.26, 0.28)
@@ -136,12 +139,13 @@ def test_im2col(cuda_device, fmt):
     u8 = torch.randint(0, 256, (b, size, size, 3), generator=g, dtype=torch.uint8)
     pv = ((u8.float() / 255.0).permute(0, 3, 1, 2) - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
     if fmt == "u8":
-        out = ops.im2col(u8.cuda(), size, p, kpad, mean, std)
+        out = ops.im2col(u8.cuda(), size, p, kpad, mean, std, dtype=dtype)
     else:
-        out = ops.im2col(pv.contiguous().cuda(), size, p, kpad)
+        out = ops.im2col(pv.contiguous().cuda(), size, p, kpad, dtype=dtype)
     gs = size // p
     ref = pv.reshape(b, 3, gs, p, gs, p).permute(0, 2, 4, 1, 3, 5).reshape(b * gs * gs, kreal)
-    torch.testing.assert_close(out[:, :kreal].float().cpu(), ref, rtol=8e-3, atol=8e-3)
+    tol = 8e-3 if dtype == torch.bfloat16 else 1e-3
+    torch.testing.assert_close(out[:, :kreal].float().cpu(), ref, rtol=tol, atol=tol)
     assert (out[:, kreal:] == 0).all()
 
 
@@ -157,8 +161,40 @@ def test_pool(cuda_device, mode, b, s, d):
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
 
 
-def test_pack_bf16(cuda_device):
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_pack_16(cuda_device, dtype):
     x = _rand((37, 588), 60)
-    out = ops.pack_bf16(x, 592)
-    assert torch.equal(out[:, :588], x.to(torch.bfloat16))  # bit-exact RNE
+    out = ops.pack_16(x, 592, dtype)
+    assert torch.equal(out[:, :588], x.to(dtype))  # bit-exact RNE
     assert (out[:, 588:] == 0).all()
+
+
+@pytest.mark.parametrize("m,n,k", [(384, 1152, 1152), (520, 4304, 1152), (777, 1152, 592), (130, 432, 144)])
+def test_gemm_fp16_operands(cuda_device, m, n, k):
+    """fp16 is the tower's default operand format (DESIGN.md numerics); same kernel, other instruction-descriptor bits."""
+    a = _rand((m, k), 70).to(torch.float16)
+    w = _rand((n, k), 71, 1 / math.sqrt(k)).to(torch.float16)
+    bias = _rand((n,), 72, 0.5)
+    h = _rand((m, n), 73)
+    ref = a.float() @ w.float().t() + bias + h
+    out = ops.gemm_tn(a, w, bias, resid=h.clone())
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-4)  # exact products, fp32 accumulate
+    out16 = ops.gemm_tn(a, w, bias, act=specs.ACT_GELU_TANH)
+    assert out16.dtype == torch.float16
+    torch.testing.assert_close(out16.float(), _act_ref(ref - h, specs.ACT_GELU_TANH), rtol=2e-3, atol=2e-3)
+
+
+def test_gemm_fp16_output_saturates(cuda_device):
+    a = torch.full((128, 64), 200.0, dtype=torch.float16, device="cuda")
+    w = torch.full((128, 64), 100.0, dtype=torch.float16, device="cuda")  # acc = 1.28e6 > 65504
+    out = ops.gemm_tn(a, w)
+    assert torch.isfinite(out.float()).all() and (out.float() == 65504.0).all()
+
+
+def test_gemm_rejects_mixed_formats(cuda_device):
+    """A and W of one tcgen05.mma kind::f16 must share a format (a bf16 x fp16 mix faults as an illegal instruction on
+    B200), so the host refuses it."""
+    a = torch.zeros(128, 64, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(128, 64, dtype=torch.float16, device="cuda")
+    with pytest.raises(TypeError):
+        ops.gemm_tn(a, w)

@@ -11,6 +11,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vlmfw_b200 import ops, specs  # noqa: E402
 
+DT = torch.float16
+
 
 def timeit(fn, iters=10, warm=3):
     for _ in range(warm):
@@ -41,20 +43,20 @@ def main():
     for name, n, k, kind in shapes:
         if args.only and args.only not in name:
             continue
-        a = (torch.randn(m, k, device=dev) * 0.5).to(torch.bfloat16)
-        w = (torch.randn(n, k, device=dev) / math.sqrt(k)).to(torch.bfloat16)
+        a = (torch.randn(m, k, device=dev) * 0.5).to(DT)
+        w = (torch.randn(n, k, device=dev) / math.sqrt(k)).to(DT)
         bias = torch.randn(n, device=dev)
         flops = 2.0 * m * n * k
         if kind == "resid":
             h = torch.randn(m, n, device=dev)
-            fn = lambda: ops.gemm_bf16(a, w, bias, resid=h, out=h, block_n=args.block_n)  # noqa: E731
+            fn = lambda: ops.gemm_tn(a, w, bias, resid=h, out=h, block_n=args.block_n)  # noqa: E731
         else:
-            out = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+            out = torch.empty(m, n, dtype=DT, device=dev)
             act = specs.ACT_GELU_TANH if kind == "gelu" else specs.ACT_NONE
-            fn = lambda: ops.gemm_bf16(a, w, bias, act=act, out=out, block_n=args.block_n)  # noqa: E731
+            fn = lambda: ops.gemm_tn(a, w, bias, act=act, out=out, block_n=args.block_n)  # noqa: E731
         med, best = timeit(fn)
         wt = w.t()
-        cb_out = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+        cb_out = torch.empty(m, n, dtype=DT, device=dev)
         cmed, cbest = timeit(lambda: torch.matmul(a, wt, out=cb_out))
         rows.append({"kernel": name, "m": m, "n": n, "k": k, "epi": kind, "ms": round(med, 4), "tflops": round(flops / med / 1e9, 1),
                      "best_tflops": round(flops / best / 1e9, 1), "cublas_ms": round(cmed, 4),
@@ -65,14 +67,14 @@ def main():
         d = 1152
         x = torch.randn(m, d, device=dev)
         g, b = torch.ones(d, device=dev), torch.zeros(d, device=dev)
-        out = torch.empty(m, d, dtype=torch.bfloat16, device=dev)
+        out = torch.empty(m, d, dtype=DT, device=dev)
         med, best = timeit(lambda: ops.layernorm(x, g, b, 1e-6, out=out))
         byts = m * d * 6
         print(json.dumps({"kernel": "layernorm", "rows": m, "dim": d, "ms": round(med, 4), "gbs": round(byts / med / 1e6, 1)}), flush=True)
     if not args.only or "att" in args.only:
         for name, s, hd, dh in [("siglip.att", 256, 16, 72), ("clip.att", 577, 16, 64), ("eva.att", 257, 16, 88)]:
             bsz = max(1, m // s)
-            qkv = (torch.randn(bsz * s, 3 * hd * dh, device=dev)).to(torch.bfloat16)
+            qkv = (torch.randn(bsz * s, 3 * hd * dh, device=dev)).to(DT)
             med, best = timeit(lambda: ops.attention(qkv, bsz, s, hd, dh))
             flops = 4.0 * bsz * hd * s * s * dh
             print(json.dumps({"kernel": name, "batch": bsz, "ms": round(med, 4), "tflops": round(flops / med / 1e9, 1)}), flush=True)

@@ -1,0 +1,39 @@
+"""One launch sequence of the hot kernels at the headline shapes (SigLIP-So400m, batch 256 -> M = 65536), for
+`ncu --set full -k regex:'gemm_bf16_tn|attention_kernel|layernorm_kernel|pool_ln_mean|im2col'`. Each kernel runs twice
+(first = warm-up: tensor maps, func attributes); profile the second with --launch-skip or read both."""
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vlmfw_b200 import ops, specs  # noqa: E402
+
+DT = torch.float16
+spec = specs.SIGLIP_SO400M
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+M, D, I = B * spec.tokens, spec.hidden, spec.mlp
+dev = "cuda"
+g = torch.Generator(device=dev).manual_seed(0)
+rn = lambda *s, sc=1.0: torch.randn(*s, device=dev, generator=g) * sc  # noqa: E731
+
+h = rn(M, D)
+gamma, beta = 1 + rn(D, sc=0.1), rn(D, sc=0.1)
+wqkv, bqkv = rn(3 * D, D, sc=1 / math.sqrt(D)).to(DT), rn(3 * D, sc=0.1)
+wo, bo = rn(D, D, sc=1 / math.sqrt(D)).to(DT), rn(D, sc=0.1)
+w1, b1 = rn(I, D, sc=1 / math.sqrt(D)).to(DT), rn(I, sc=0.1)
+w2, b2 = rn(D, I, sc=1 / math.sqrt(I)).to(DT), rn(D, sc=0.1)
+pix = torch.randint(0, 256, (B, 224, 224, 3), device=dev, dtype=torch.uint8, generator=g)
+
+for it in range(2):
+    a = ops.im2col(pix, 224, 14, 592, spec.pix_mean, spec.pix_std, dtype=DT)
+    xn = ops.layernorm(h, gamma, beta, 1e-6, dtype=DT)
+    qkv = ops.gemm_tn(xn, wqkv, bqkv)
+    ctx = ops.attention(qkv, B, spec.tokens, spec.heads, spec.head_dim)
+    ops.gemm_tn(ctx, wo, bo, resid=h, out=h)
+    mid = ops.gemm_tn(xn, w1, b1, act=spec.act)
+    ops.gemm_tn(mid, w2, b2, resid=h, out=h)
+    pooled = ops.pool(h.view(B, spec.tokens, D), specs.POOL_LN_MEAN, gamma, beta, 1e-6)
+    torch.cuda.synchronize()
+print("ok", float(pooled.float().abs().mean()))

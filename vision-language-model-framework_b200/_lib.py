@@ -15,6 +15,9 @@ LIB_PATH = os.path.join(_HERE, "libvlmfw_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 OK, E_INVALID, E_NODEVICE, E_CUDA, E_STATE, E_NOTFOUND = 0, -1, -2, -3, -4, -5
+E_RANGE = -6
+DT_BF16, DT_F16, DT_F32 = 0, 1, 2
+CDT_F16, CDT_BF16 = 0, 1
 
 
 class VlmfwError(RuntimeError):
@@ -28,7 +31,7 @@ class TowerCfg(C.Structure):
         ("arch", C.c_int32), ("image_size", C.c_int32), ("patch_size", C.c_int32), ("hidden", C.c_int32),
         ("heads", C.c_int32), ("mlp", C.c_int32), ("layers", C.c_int32), ("has_cls", C.c_int32),
         ("has_pre_ln", C.c_int32), ("conv_bias", C.c_int32), ("act", C.c_int32), ("pool", C.c_int32),
-        ("ln_eps", C.c_float), ("pix_mean", C.c_float * 3), ("pix_std", C.c_float * 3),
+        ("ln_eps", C.c_float), ("pix_mean", C.c_float * 3), ("pix_std", C.c_float * 3), ("compute_dtype", C.c_int32),
     ]
 
 
@@ -63,13 +66,13 @@ SIGNATURES = {
                                            _vp, _f32, _vp, _vp, _vp, _vp]),
     "vlmfw_probe_adamw": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "vlmfw_probe_bn_running_update": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, _vp]),
-    "vlmfw_gemm_bf16": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
-                                  _i32, _i32, _i32, _i32, _i32, _vp]),
+    "vlmfw_gemm_tn": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
+                                _i32, _i32, _i32, _i32, _i32, _vp]),
     "vlmfw_layernorm": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _f32, _vp, _i32, _vp]),
-    "vlmfw_attention": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "vlmfw_im2col": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), C.POINTER(_f32), _vp, _i32, _vp]),
+    "vlmfw_attention": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "vlmfw_im2col": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), C.POINTER(_f32), _vp, _i32, _i32, _vp]),
     "vlmfw_pool": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp]),
-    "vlmfw_pack_bf16": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp]),
+    "vlmfw_pack_16": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i32, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

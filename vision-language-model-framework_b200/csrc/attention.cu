@@ -46,7 +46,7 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* smem_tile, const __nv_b
     }
 }
 
-template <int DHP>
+template <int DHP, bool F16>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                 __nv_bfloat16* __restrict__ out, int tokens,
                                                                 int heads, int dh, float scale_log2) {
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __nv_bfloa
                 const int key = np * 16 + (lane & 7) + (lane >> 4) * 8;
                 const int c = kk * 16 + ((lane >> 3) & 1) * 8;
                 ldmatrix_x4(smem_u32(kb + key * C::PITCH + c), b0, b1, b2, b3);
-                mma_bf16_16816(s[2 * np], qf[kk], b0, b1);
-                mma_bf16_16816(s[2 * np + 1], qf[kk], b2, b3);
+                mma_16816<F16>(s[2 * np], qf[kk], b0, b1);
+                mma_16816<F16>(s[2 * np + 1], qf[kk], b2, b3);
             }
         }
         // ---- mask the ragged tail, online softmax (rows g and g+8 of this warp's 16)
@@ -174,18 +174,18 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __nv_bfloa
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
             uint32_t pa[4];
-            pa[0] = pack_bf16x2(s[2 * ks][0], s[2 * ks][1]);
-            pa[1] = pack_bf16x2(s[2 * ks][2], s[2 * ks][3]);
-            pa[2] = pack_bf16x2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
-            pa[3] = pack_bf16x2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+            pa[0] = pack_16x2<F16>(s[2 * ks][0], s[2 * ks][1]);
+            pa[1] = pack_16x2<F16>(s[2 * ks][2], s[2 * ks][3]);
+            pa[2] = pack_16x2<F16>(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+            pa[3] = pack_16x2<F16>(s[2 * ks + 1][2], s[2 * ks + 1][3]);
 #pragma unroll
             for (int np = 0; np < NT_O / 2; ++np) {
                 uint32_t b0, b1, b2, b3;
                 const int key = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
                 const int c = np * 16 + (lane >> 4) * 8;
                 ldmatrix_x4_trans(smem_u32(vb + key * C::PITCH + c), b0, b1, b2, b3);
-                mma_bf16_16816(o[2 * np], pa, b0, b1);
-                mma_bf16_16816(o[2 * np + 1], pa, b2, b3);
+                mma_16816<F16>(o[2 * np], pa, b0, b1);
+                mma_16816<F16>(o[2 * np + 1], pa, b2, b3);
             }
         }
         __syncthreads();  // everyone is done with `buf` before the next prefetch overwrites buf^1's partner
@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __nv_bfloa
 #pragma unroll
         for (int i = 0; i < NT_O; ++i) {
             const int c = i * 8 + 2 * t;
-            *reinterpret_cast<uint32_t*>(sQ + r0 * C::PITCH + c) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
-            *reinterpret_cast<uint32_t*>(sQ + (r0 + 8) * C::PITCH + c) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+            *reinterpret_cast<uint32_t*>(sQ + r0 * C::PITCH + c) = pack_16x2<F16>(o[i][0] * inv0, o[i][1] * inv0);
+            *reinterpret_cast<uint32_t*>(sQ + (r0 + 8) * C::PITCH + c) = pack_16x2<F16>(o[i][2] * inv1, o[i][3] * inv1);
         }
     }
     __syncthreads();
@@ -219,10 +219,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __nv_bfloa
     }
 }
 
-template <int DHP>
+template <int DHP, bool F16>
 int launch_att(const void* qkv, int batch, int tokens, int heads, int dh, void* out, cudaStream_t stream) {
     using C = AttCfg<DHP>;
-    auto kern = attention_kernel<DHP>;
+    auto kern = attention_kernel<DHP, F16>;
     static bool attr_set = false;
     if (!attr_set) {
         VLMFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -238,16 +238,22 @@ int launch_att(const void* qkv, int batch, int tokens, int heads, int dh, void* 
 
 }  // namespace
 
-int launch_attention(const void* qkv, int batch, int tokens, int heads, int head_dim, void* out, cudaStream_t stream) {
+int launch_attention(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out,
+                     cudaStream_t stream) {
     VLMFW_REQUIRE(qkv && out, "attention: null pointer");
     VLMFW_REQUIRE(batch > 0 && tokens > 0 && heads > 0, "attention: bad shape");
     VLMFW_REQUIRE(head_dim % 8 == 0 && head_dim >= 8 && head_dim <= 96, "attention: head_dim %d unsupported", head_dim);
     VLMFW_REQUIRE(batch <= 65535 && heads <= 65535, "attention: grid too large");
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
-    if (head_dim <= 64) return launch_att<64>(qkv, batch, tokens, heads, head_dim, out, stream);
-    if (head_dim <= 80) return launch_att<80>(qkv, batch, tokens, heads, head_dim, out, stream);
-    return launch_att<96>(qkv, batch, tokens, heads, head_dim, out, stream);
+    if (f16) {
+        if (head_dim <= 64) return launch_att<64, true>(qkv, batch, tokens, heads, head_dim, out, stream);
+        if (head_dim <= 80) return launch_att<80, true>(qkv, batch, tokens, heads, head_dim, out, stream);
+        return launch_att<96, true>(qkv, batch, tokens, heads, head_dim, out, stream);
+    }
+    if (head_dim <= 64) return launch_att<64, false>(qkv, batch, tokens, heads, head_dim, out, stream);
+    if (head_dim <= 80) return launch_att<80, false>(qkv, batch, tokens, heads, head_dim, out, stream);
+    return launch_att<96, false>(qkv, batch, tokens, heads, head_dim, out, stream);
 }
 
 }  // namespace vlmfw

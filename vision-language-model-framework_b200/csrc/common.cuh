@@ -54,20 +54,24 @@ struct GemmArgs {
     int resid_mod = 0;
     int grp = 0, grp_out = 0, grp_off = 0;
     int block_n = 0;  // 0 = pick automatically
+    bool f16 = false;  // 16-bit format of A, W and the 16-bit output: false = bf16, true = fp16 (A and W must agree)
 };
 
 int device_check();
 int num_sms();
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
 int launch_layernorm(const float* x, int rows, int dim, const float* gamma, const float* beta, float eps, void* out,
-                     bool out_f32, cudaStream_t stream);
-int launch_attention(const void* qkv, int batch, int tokens, int heads, int head_dim, void* out, cudaStream_t stream);
+                     int out_dtype, cudaStream_t stream);
+int launch_attention(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out,
+                     cudaStream_t stream);
 int launch_im2col(const void* pixels, int pix_fmt, int batch, int image_size, int patch, const float* mean3,
-                  const float* std3, void* out, int kpad, cudaStream_t stream);
+                  const float* std3, void* out, int kpad, bool out_f16, cudaStream_t stream);
 int launch_fill_cls(const float* cls_pos0, float* h, int batch, int tokens, int dim, cudaStream_t stream);
 int launch_pool(const float* h, int batch, int tokens, int dim, int pool, const float* gamma, const float* beta,
                 float eps, float* pooled, cudaStream_t stream);
-int launch_pack_bf16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, cudaStream_t stream);
+int launch_pack_16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, bool f16, cudaStream_t stream);
+// max |x| over a device fp32 array, returned to the host (synchronises `stream`; load-time only)
+int device_absmax(const float* src, int64_t numel, float* host_out, cudaStream_t stream);
 int launch_add_rows(const float* a, const float* b, float* out, int64_t rows, int64_t cols, int64_t a_row0,
                     cudaStream_t stream);
 

@@ -6,6 +6,8 @@
 //                   fused here when the input is raw uint8.
 //   fill_cls      : class_embedding + position_embedding[0] written to token 0 of every image
 //                   (modeling_clip.py:208-217, modeling_blip_2.py:247-255)
+#include <cstring>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -18,9 +20,9 @@ struct PixNorm {
 };
 
 // One thread produces 8 consecutive k of one patch row (16-byte store).
-template <int PIX_FMT>
+template <int PIX_FMT, bool OUT_F16>
 __global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ pixels, int batch, int img, int patch,
-                                                     PixNorm nrm, __nv_bfloat16* __restrict__ out, int kpad) {
+                                                     PixNorm nrm, uint16_t* __restrict__ out, int kpad) {
     const int grid_side = img / patch;
     const int patches = grid_side * grid_side;
     const int kreal = 3 * patch * patch;
@@ -55,10 +57,10 @@ __global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ pi
             f[j] = val;
         }
         uint4 o;
-        o.x = pack_bf16x2(f[0], f[1]);
-        o.y = pack_bf16x2(f[2], f[3]);
-        o.z = pack_bf16x2(f[4], f[5]);
-        o.w = pack_bf16x2(f[6], f[7]);
+        o.x = pack_16x2<OUT_F16>(f[0], f[1]);
+        o.y = pack_16x2<OUT_F16>(f[2], f[3]);
+        o.z = pack_16x2<OUT_F16>(f[4], f[5]);
+        o.w = pack_16x2<OUT_F16>(f[6], f[7]);
         *reinterpret_cast<uint4*>(out + row * kpad + g * 8) = o;
     }
 }
@@ -70,14 +72,28 @@ __global__ void fill_cls_kernel(const float* __restrict__ cls_pos0, float* __res
         h[static_cast<size_t>(b) * tokens * dim + d] = cls_pos0[d];
 }
 
-__global__ void pack_bf16_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, __nv_bfloat16* dst,
-                                 int64_t dst_ld) {
+template <bool F16>
+__global__ void pack_16_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, uint16_t* dst,
+                               int64_t dst_ld) {
     const int64_t total = rows * dst_ld;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t r = i / dst_ld, c = i - r * dst_ld;
-        dst[i] = __float2bfloat16_rn(c < cols ? src[r * cols + c] : 0.f);
+        const float v = c < cols ? src[r * cols + c] : 0.f;
+        if constexpr (F16) dst[i] = __half_as_ushort(__float2half_rn(v));
+        else dst[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
     }
+}
+
+// max |x| via a bit-pattern atomicMax (non-negative floats order like unsigned ints); NaN/Inf map above any finite
+__global__ void absmax_kernel(const float* __restrict__ src, int64_t numel, unsigned int* out) {
+    unsigned int m = 0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < numel;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        m = max(m, __float_as_uint(src[i]) & 0x7FFFFFFFu);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
 // out[r, c] = a[r + a_row0, c] + (b ? b[c] : 0)
@@ -100,11 +116,13 @@ int grid_for(size_t total, int threads) {
 }  // namespace
 
 int launch_im2col(const void* pixels, int pix_fmt, int batch, int image_size, int patch, const float* mean3,
-                  const float* std3, void* out, int kpad, cudaStream_t stream) {
+                  const float* std3, void* out, int kpad, bool out_f16, cudaStream_t stream) {
     VLMFW_REQUIRE(pixels && out, "im2col: null pointer");
     VLMFW_REQUIRE(batch > 0 && patch > 0 && image_size % patch == 0, "im2col: image %d not a multiple of patch %d",
                   image_size, patch);
     VLMFW_REQUIRE(kpad % 8 == 0 && kpad >= 3 * patch * patch, "im2col: kpad %d too small / unaligned", kpad);
+    VLMFW_REQUIRE(pix_fmt == VLMFW_PIX_U8_NHWC || pix_fmt == VLMFW_PIX_F32_NCHW, "im2col: unknown pixel format %d",
+                  pix_fmt);
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
     PixNorm nrm;
@@ -117,15 +135,14 @@ int launch_im2col(const void* pixels, int pix_fmt, int batch, int image_size, in
     const int g = image_size / patch;
     const size_t total = static_cast<size_t>(batch) * g * g * (kpad / 8);
     const int threads = 256;
-    if (pix_fmt == VLMFW_PIX_U8_NHWC)
-        im2col_kernel<VLMFW_PIX_U8_NHWC><<<grid_for(total, threads), threads, 0, stream>>>(
-            pixels, batch, image_size, patch, nrm, static_cast<__nv_bfloat16*>(out), kpad);
-    else if (pix_fmt == VLMFW_PIX_F32_NCHW)
-        im2col_kernel<VLMFW_PIX_F32_NCHW><<<grid_for(total, threads), threads, 0, stream>>>(
-            pixels, batch, image_size, patch, nrm, static_cast<__nv_bfloat16*>(out), kpad);
-    else {
-        set_error("im2col: unknown pixel format %d", pix_fmt);
-        return VLMFW_E_INVALID;
+    const int grid = grid_for(total, threads);
+    uint16_t* o = static_cast<uint16_t*>(out);
+    if (pix_fmt == VLMFW_PIX_U8_NHWC) {
+        if (out_f16) im2col_kernel<VLMFW_PIX_U8_NHWC, true><<<grid, threads, 0, stream>>>(pixels, batch, image_size, patch, nrm, o, kpad);
+        else im2col_kernel<VLMFW_PIX_U8_NHWC, false><<<grid, threads, 0, stream>>>(pixels, batch, image_size, patch, nrm, o, kpad);
+    } else {
+        if (out_f16) im2col_kernel<VLMFW_PIX_F32_NCHW, true><<<grid, threads, 0, stream>>>(pixels, batch, image_size, patch, nrm, o, kpad);
+        else im2col_kernel<VLMFW_PIX_F32_NCHW, false><<<grid, threads, 0, stream>>>(pixels, batch, image_size, patch, nrm, o, kpad);
     }
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
@@ -137,13 +154,32 @@ int launch_fill_cls(const float* cls_pos0, float* h, int batch, int tokens, int 
     return VLMFW_OK;
 }
 
-int launch_pack_bf16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, cudaStream_t stream) {
-    VLMFW_REQUIRE(src && dst && rows > 0 && cols > 0 && dst_ld >= cols, "pack_bf16: bad arguments");
+int launch_pack_16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, bool f16, cudaStream_t stream) {
+    VLMFW_REQUIRE(src && dst && rows > 0 && cols > 0 && dst_ld >= cols, "pack_16: bad arguments");
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
-    pack_bf16_kernel<<<grid_for(static_cast<size_t>(rows * dst_ld), 256), 256, 0, stream>>>(
-        src, rows, cols, static_cast<__nv_bfloat16*>(dst), dst_ld);
+    const int grid = grid_for(static_cast<size_t>(rows * dst_ld), 256);
+    if (f16) pack_16_kernel<true><<<grid, 256, 0, stream>>>(src, rows, cols, static_cast<uint16_t*>(dst), dst_ld);
+    else pack_16_kernel<false><<<grid, 256, 0, stream>>>(src, rows, cols, static_cast<uint16_t*>(dst), dst_ld);
     VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+int device_absmax(const float* src, int64_t numel, float* host_out, cudaStream_t stream) {
+    VLMFW_REQUIRE(src && host_out && numel > 0, "absmax: bad arguments");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    unsigned int* d = nullptr;
+    VLMFW_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d), sizeof(unsigned int)));
+    VLMFW_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(unsigned int), stream));
+    absmax_kernel<<<grid_for(static_cast<size_t>(numel), 256), 256, 0, stream>>>(src, numel, d);
+    ++launch_counter();
+    unsigned int bits = 0;
+    cudaError_t e = cudaMemcpyAsync(&bits, d, sizeof(bits), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    VLMFW_CUDA_OK(e);
+    memcpy(host_out, &bits, sizeof(float));
     return VLMFW_OK;
 }
 

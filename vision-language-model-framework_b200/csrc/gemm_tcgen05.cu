@@ -1,6 +1,6 @@
 // bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM), fed by TMA.
 //
-//   out = epilogue( A[M,K] * W[N,K]^T )        A, W bf16 row-major (both K-major), fp32 accumulate
+//   out = epilogue( A[M,K] * W[N,K]^T )        A, W 16-bit row-major (both K-major; each bf16 or fp16), fp32 accumulate
 //
 // This one kernel carries every dense contraction of the tower (reference path: the nn.Linear / Conv2d calls inside
 // transformers' SiglipEncoderLayer / CLIPEncoderLayer / Blip2EncoderLayer):
@@ -46,6 +46,8 @@ struct Cfg {
 
 struct KParams {
     int m, n, k;
+    uint32_t idesc;  // tcgen05 instruction descriptor (the operand format is a run-time choice)
+    int out_f16;     // 16-bit epilogue output format
     const float* bias;
     void* out;
     int ldo;
@@ -140,7 +142,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            const uint32_t idesc = p.idesc;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -187,6 +189,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int cj = lane & 7;     // read-back: 16-byte column group (4 fp32)
         int acc = 0;
         uint32_t acc_phase = 0;
+
+        // Residual epilogue: the fp32 residual tile is the only global READ of the epilogue and it does not depend on
+        // the accumulator, so it is software-pipelined one 32-column chunk ahead (across tile boundaries too): the
+        // loads of chunk i+1 are in flight while chunk i waits for TMEM / transposes / stores.
+        float4 rnext[8];
+        auto resid_issue = [&](int tile, int c, float4 (&r)[8]) {
+            if constexpr (EPI == VLMFW_EPI_BIAS_RESID_F32) {
+                const int m0 = (tile / n_tiles) * BM + quarter * 32;
+                const int col = (tile % n_tiles) * BN + half * COLS_PER_WARP + c * 32 + cj * 4;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int row = m0 + it * 4 + rsub;
+                    r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < p.m && col < p.n) {
+                        const int rrow = (p.resid_mod > 0) ? (row % p.resid_mod) : row;
+                        r[it] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(rrow) * p.ldr + col);
+                    }
+                }
+            }
+        };
+        if (blockIdx.x < num_tiles) resid_issue(blockIdx.x, 0, rnext);
+
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * BM + quarter * 32;
             const int n0 = (tile % n_tiles) * BN + half * COLS_PER_WARP;
@@ -195,7 +219,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 1
             for (int c = 0; c < CHUNKS; ++c) {
                 const int nc = n0 + c * 32;
-                if (nc >= p.n) break;  // warp-uniform: whole chunk is past the N edge
+                float4 rcur[8];
+                if constexpr (EPI == VLMFW_EPI_BIAS_RESID_F32) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) rcur[it] = rnext[it];
+                    // next chunk of this tile, or chunk 0 of this CTA's next tile
+                    if (c + 1 < CHUNKS) resid_issue(tile, c + 1, rnext);
+                    else if (tile + static_cast<int>(gridDim.x) < num_tiles) resid_issue(tile + gridDim.x, 0, rnext);
+                }
+                if (nc >= p.n) continue;  // warp-uniform: whole chunk is past the N edge (prefetch above still ran)
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                        static_cast<uint32_t>(acc * BN + half * COLS_PER_WARP + c * 32);
@@ -231,19 +263,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         int orow = row;
                         if (p.grp > 0) orow = (row / p.grp) * p.grp_out + (row % p.grp) + p.grp_off;
                         if constexpr (EPI == VLMFW_EPI_BIAS_RESID_F32) {
-                            const int rrow = (p.resid_mod > 0) ? (row % p.resid_mod) : row;
-                            const float4 r =
-                                *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(rrow) * p.ldr + col);
-                            a.x += r.x;
-                            a.y += r.y;
-                            a.z += r.z;
-                            a.w += r.w;
+                            a.x += rcur[it].x;
+                            a.y += rcur[it].y;
+                            a.z += rcur[it].z;
+                            a.w += rcur[it].w;
                             *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(orow) * p.ldo +
                                                        col) = a;
                         } else {
                             uint2 o;
-                            o.x = pack_bf16x2(activation<ACT>(a.x), activation<ACT>(a.y));
-                            o.y = pack_bf16x2(activation<ACT>(a.z), activation<ACT>(a.w));
+                            const float y0 = activation<ACT>(a.x), y1 = activation<ACT>(a.y);
+                            const float y2 = activation<ACT>(a.z), y3 = activation<ACT>(a.w);
+                            o.x = p.out_f16 ? pack_f16x2(y0, y1) : pack_bf16x2(y0, y1);
+                            o.y = p.out_f16 ? pack_f16x2(y2, y3) : pack_bf16x2(y2, y3);
                             *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) +
                                                       static_cast<size_t>(orow) * p.ldo + col) = o;
                         }
@@ -288,9 +319,9 @@ EncodeTiledFn encode_fn() {
 
 struct MapKey {
     const void* ptr;
-    int rows, cols, ld, box_rows;
+    int rows, cols, ld, box_rows, f16;
     bool operator==(const MapKey& o) const {
-        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && f16 == o.f16;
     }
 };
 struct MapKeyHash {
@@ -299,17 +330,17 @@ struct MapKeyHash {
         h ^= (static_cast<size_t>(k.rows) * 0x9E3779B97F4A7C15ull) + (h << 6) + (h >> 2);
         h ^= (static_cast<size_t>(k.cols) * 0xC2B2AE3D27D4EB4Full) + (h << 6) + (h >> 2);
         h ^= (static_cast<size_t>(k.ld) * 0x165667B19E3779F9ull) + (h << 6) + (h >> 2);
-        h ^= static_cast<size_t>(k.box_rows) + (h << 6) + (h >> 2);
+        h ^= static_cast<size_t>(k.box_rows * 2 + k.f16) + (h << 6) + (h >> 2);
         return h;
     }
 };
 
 // [rows, cols] bf16 row-major (row stride ld elements) -> tiled map with box {64 cols, box_rows}, 128B swizzle,
 // out-of-bounds elements read as zero (this is what makes ragged M / N / K edges free).
-int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, bool f16, CUtensorMap* out) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    MapKey key{ptr, rows, cols, ld, box_rows};
+    MapKey key{ptr, rows, cols, ld, box_rows, f16 ? 1 : 0};
     {
         std::lock_guard<std::mutex> lk(mu);
         auto it = cache.find(key);
@@ -328,7 +359,7 @@ int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, CU
     cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estride[2] = {1, 1};
     CUtensorMap tm;
-    CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estride,
+    CUresult r = fn(&tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estride,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -349,9 +380,9 @@ template <int BN, int EPI, int ACT>
 int launch_one(const GemmArgs& g, cudaStream_t stream) {
     using C = Cfg<BN>;
     CUtensorMap ta, tw;
-    int rc = get_tensor_map(g.a, g.m, g.k, g.lda, BM, &ta);
+    int rc = get_tensor_map(g.a, g.m, g.k, g.lda, BM, g.f16, &ta);
     if (rc != VLMFW_OK) return rc;
-    rc = get_tensor_map(g.w, g.n, g.k, g.ldw, BN, &tw);
+    rc = get_tensor_map(g.w, g.n, g.k, g.ldw, BN, g.f16, &tw);
     if (rc != VLMFW_OK) return rc;
     auto kern = gemm_bf16_tn_kernel<BN, EPI, ACT>;
     static bool attr_set = false;
@@ -363,6 +394,8 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
     p.m = g.m;
     p.n = g.n;
     p.k = g.k;
+    p.idesc = umma_idesc_16(BM, BN, g.f16, g.f16);
+    p.out_f16 = g.f16 ? 1 : 0;
     p.bias = g.bias;
     p.out = g.out;
     p.ldo = g.ldo;

@@ -16,7 +16,7 @@ namespace {
 constexpr int LN_MAX_CHUNKS = 12;  // float4 chunks per lane: dim <= 12*32*4 = 1536
 
 // One warp per row. dim % 4 == 0.
-template <bool OUT_F32>
+template <int OUT_DT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int rows, int dim,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, void* out) {
@@ -59,13 +59,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
             y.y = (v[i].y - mean) * rstd * g.y + b.y;
             y.z = (v[i].z - mean) * rstd * g.z + b.z;
             y.w = (v[i].w - mean) * rstd * g.w + b.w;
-            if constexpr (OUT_F32) {
+            if constexpr (OUT_DT == VLMFW_DT_F32) {
                 reinterpret_cast<float4*>(static_cast<float*>(out) + static_cast<size_t>(warp) * dim)[c] = y;
             } else {
                 uint2 o;
-                o.x = pack_bf16x2(y.x, y.y);
-                o.y = pack_bf16x2(y.z, y.w);
-                reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + static_cast<size_t>(warp) * dim)[c] = o;
+                o.x = pack_16x2<OUT_DT == VLMFW_DT_F16>(y.x, y.y);
+                o.y = pack_16x2<OUT_DT == VLMFW_DT_F16>(y.z, y.w);
+                reinterpret_cast<uint2*>(static_cast<uint16_t*>(out) + static_cast<size_t>(warp) * dim)[c] = o;
             }
         }
     }
@@ -193,17 +193,23 @@ __global__ void __launch_bounds__(128) pool_cls_ln2_kernel(const float* __restri
 }  // namespace
 
 int launch_layernorm(const float* x, int rows, int dim, const float* gamma, const float* beta, float eps, void* out,
-                     bool out_f32, cudaStream_t stream) {
+                     int out_dtype, cudaStream_t stream) {
     VLMFW_REQUIRE(x && gamma && beta && out, "layernorm: null pointer");
     VLMFW_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAX_CHUNKS * 128, "layernorm: bad dim %d", dim);
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
     const int warps_per_block = 8;
     const int grid = (rows + warps_per_block - 1) / warps_per_block;
-    if (out_f32)
-        layernorm_kernel<true><<<grid, warps_per_block * 32, 0, stream>>>(x, rows, dim, gamma, beta, eps, out);
-    else
-        layernorm_kernel<false><<<grid, warps_per_block * 32, 0, stream>>>(x, rows, dim, gamma, beta, eps, out);
+    if (out_dtype == VLMFW_DT_F32)
+        layernorm_kernel<VLMFW_DT_F32><<<grid, warps_per_block * 32, 0, stream>>>(x, rows, dim, gamma, beta, eps, out);
+    else if (out_dtype == VLMFW_DT_F16)
+        layernorm_kernel<VLMFW_DT_F16><<<grid, warps_per_block * 32, 0, stream>>>(x, rows, dim, gamma, beta, eps, out);
+    else if (out_dtype == VLMFW_DT_BF16)
+        layernorm_kernel<VLMFW_DT_BF16><<<grid, warps_per_block * 32, 0, stream>>>(x, rows, dim, gamma, beta, eps, out);
+    else {
+        set_error("layernorm: unknown out_dtype %d", out_dtype);
+        return VLMFW_E_INVALID;
+    }
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }

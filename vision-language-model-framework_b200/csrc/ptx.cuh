@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace vlmfw {
 
@@ -94,11 +95,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
-// Instruction descriptor, kind::f16, A/B = bf16 (K-major both), D = fp32.
-//   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt  [15] A major  [16] B major
+// Instruction descriptor, kind::f16, A/B K-major, D = fp32. a_f16 / b_f16 pick the 16-bit format PER OPERAND
+// (0 = bf16, 1 = fp16): the tower multiplies bf16 activations by fp16 weights (numerics).
+//   [4,6) D fmt (1 = f32)  [7,10) A fmt (0 = f16, 1 = bf16)  [10,13) B fmt  [15] A major  [16] B major
 //   [17,23) N >> 3   [24,29) M >> 4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+__host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, bool a_f16, bool b_f16) {
+    return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
@@ -170,9 +172,34 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// D(16x8, f32) += A(16x16, f16 row) * B(16x8, f16 col)
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool F16>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if constexpr (F16) mma_f16_16816(d, a, b0, b1);
+    else mma_bf16_16816(d, a, b0, b1);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+// saturating: |x| > 65504 stores +-65504 instead of inf, so one large activation cannot turn a row into NaNs
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
+    if constexpr (F16) return pack_f16x2(lo, hi);
+    else return pack_bf16x2(lo, hi);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -7,10 +7,10 @@
 // HBM layout per forward (M = B*S tokens), all inside one caller-provided workspace:
 //   h    fp32 [M, D]    residual stream — kept in fp32 end to end (bf16 residuals miss the
 //                       1e-2 logit tolerance); read by LayerNorm, read-modify-written by the out-proj / fc2 epilogues
-//   xn   bf16 [M, D]    LayerNorm output = A operand of the QKV / fc1 GEMMs
-//   qkv  bf16 [M, 3D]   fused projection, consumed in place by the attention kernel (no head permute)
-//   ctx  bf16 [M, D]    attention output = A operand of out-proj
-//   mid  bf16 [M, I]    GELU(fc1) = A operand of fc2; the patch-gather matrix [B*P, 592] aliases it before layer 0
+//   xn   16b  [M, D]    LayerNorm output = A operand of the QKV / fc1 GEMMs (16b = fp16 or bf16, cfg.compute_dtype)
+//   qkv  16b  [M, 3D]   fused projection, consumed in place by the attention kernel (no head permute)
+//   ctx  16b  [M, D]    attention output = A operand of out-proj
+//   mid  16b  [M, I]    GELU(fc1) = A operand of fc2; the patch-gather matrix [B*P, 592] aliases it before layer 0
 #include <cstdarg>
 #include <cstring>
 #include <string>
@@ -89,7 +89,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Slot {
     void** dst = nullptr;
-    bool matrix = false;  // repack to bf16 [rows, ld]
+    bool matrix = false;  // repack to fp16 / bf16 [rows, ld]
     int64_t rows = 0, cols = 0, ld = 0;
     bool required = true;
     bool set = false;
@@ -107,7 +107,8 @@ struct vlmfw_tower {
     vlmfw_tower_cfg cfg{};
     int P = 0, S = 0, D = 0, H = 0, dh = 0, I = 0, L = 0, kreal = 0, kpad = 0;
     std::vector<LayerW> layers;
-    void* patch_w = nullptr;  // bf16 [D, kpad]
+    void* patch_w = nullptr;  // 16-bit [D, kpad]
+    bool f16 = true;  // cfg.compute_dtype == VLMFW_CDT_F16
     float* patch_b = nullptr;
     float* cls = nullptr;
     float* pos = nullptr;  // [S, D]
@@ -168,6 +169,8 @@ extern "C" int vlmfw_tower_create(const vlmfw_tower_cfg* cfg, vlmfw_tower** out)
     VLMFW_REQUIRE(cfg->layers > 0, "tower_create: layers %d", cfg->layers);
     VLMFW_REQUIRE(cfg->act >= VLMFW_ACT_GELU_TANH && cfg->act <= VLMFW_ACT_GELU_ERF, "tower_create: act %d", cfg->act);
     VLMFW_REQUIRE(cfg->pool >= VLMFW_POOL_LN_MEAN && cfg->pool <= VLMFW_POOL_LN_CLS_LN, "tower_create: pool %d", cfg->pool);
+    VLMFW_REQUIRE(cfg->compute_dtype == VLMFW_CDT_F16 || cfg->compute_dtype == VLMFW_CDT_BF16,
+                  "tower_create: compute_dtype %d", cfg->compute_dtype);
     if (cfg->pool == VLMFW_POOL_CLS || cfg->pool == VLMFW_POOL_LN_CLS_LN)
         VLMFW_REQUIRE(cfg->has_cls, "tower_create: CLS pooling needs has_cls");
     int rc = device_check();
@@ -175,6 +178,7 @@ extern "C" int vlmfw_tower_create(const vlmfw_tower_cfg* cfg, vlmfw_tower** out)
 
     vlmfw_tower* t = new vlmfw_tower();
     t->cfg = *cfg;
+    t->f16 = cfg->compute_dtype == VLMFW_CDT_F16;
     const int g = cfg->image_size / cfg->patch_size;
     t->P = g * g;
     t->S = t->P + (cfg->has_cls ? 1 : 0);
@@ -245,7 +249,17 @@ extern "C" int vlmfw_tower_set_weight(vlmfw_tower* t, const char* name, const fl
         VLMFW_CUDA_OK(cudaMalloc(s.dst, bytes));
     }
     if (s.matrix) {
-        int rc = launch_pack_bf16(src, s.rows, s.cols, *s.dst, s.ld, st);
+        if (t->f16) {
+            float amax = 0.f;
+            int rc = device_absmax(src, numel, &amax, st);
+            if (rc != VLMFW_OK) return rc;
+            if (!(amax < 6.0e4f)) {  // also catches NaN / Inf (bit pattern above any finite value)
+                set_error("tower_set_weight: '%s' has max |w| = %g, outside the fp16 range; recreate the tower with "
+                          "compute_dtype = VLMFW_CDT_BF16", name, static_cast<double>(amax));
+                return VLMFW_E_RANGE;
+            }
+        }
+        int rc = launch_pack_16(src, s.rows, s.cols, *s.dst, s.ld, t->f16, st);
         if (rc != VLMFW_OK) return rc;
     } else {
         VLMFW_CUDA_OK(cudaMemcpyAsync(*s.dst, src, static_cast<size_t>(numel) * 4, cudaMemcpyDeviceToDevice, st));
@@ -316,15 +330,17 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
     void* patch_a = mid;
     const int D = t->D, I = t->I, S = t->S, P = t->P;
     const int M = batch * S;
+    const int act_dt = t->f16 ? VLMFW_DT_F16 : VLMFW_DT_BF16;
 
     // ---- embeddings: conv-as-GEMM (+bias +position embedding), class token, optional pre-LN
     rc = launch_im2col(pixels, pix_fmt, batch, t->cfg.image_size, t->cfg.patch_size, t->cfg.pix_mean, t->cfg.pix_std,
-                       patch_a, t->kpad, st);
+                       patch_a, t->kpad, t->f16, st);
     if (rc != VLMFW_OK) return rc;
     {
         GemmArgs g;
         g.a = patch_a;
         g.lda = t->kpad;
+        g.f16 = t->f16;
         g.w = t->patch_w;
         g.ldw = t->kpad;
         g.m = batch * P;
@@ -347,18 +363,19 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         if (rc != VLMFW_OK) return rc;
     }
     if (t->cfg.has_pre_ln) {
-        rc = launch_layernorm(h, M, D, t->pre_w, t->pre_b, t->cfg.ln_eps, h, true, st);
+        rc = launch_layernorm(h, M, D, t->pre_w, t->pre_b, t->cfg.ln_eps, h, VLMFW_DT_F32, st);
         if (rc != VLMFW_OK) return rc;
     }
     // ---- encoder layers (pre-LN transformer blocks)
     for (int li = 0; li < t->L; ++li) {
         const LayerW& w = t->layers[li];
-        rc = launch_layernorm(h, M, D, w.ln1w, w.ln1b, t->cfg.ln_eps, xn, false, st);
+        rc = launch_layernorm(h, M, D, w.ln1w, w.ln1b, t->cfg.ln_eps, xn, act_dt, st);
         if (rc != VLMFW_OK) return rc;
         GemmArgs g;
         g.a = xn;
         g.lda = D;
         g.w = w.wqkv;
+        g.f16 = t->f16;
         g.ldw = D;
         g.m = M;
         g.n = 3 * D;
@@ -370,12 +387,13 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.ldo = 3 * D;
         rc = launch_gemm(g, st);
         if (rc != VLMFW_OK) return rc;
-        rc = launch_attention(qkv, batch, S, t->H, t->dh, ctx, st);
+        rc = launch_attention(qkv, t->f16, batch, S, t->H, t->dh, ctx, st);
         if (rc != VLMFW_OK) return rc;
         g = GemmArgs();
         g.a = ctx;
         g.lda = D;
         g.w = w.wo;
+        g.f16 = t->f16;
         g.ldw = D;
         g.m = M;
         g.n = D;
@@ -388,12 +406,13 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.ldr = D;
         rc = launch_gemm(g, st);
         if (rc != VLMFW_OK) return rc;
-        rc = launch_layernorm(h, M, D, w.ln2w, w.ln2b, t->cfg.ln_eps, xn, false, st);
+        rc = launch_layernorm(h, M, D, w.ln2w, w.ln2b, t->cfg.ln_eps, xn, act_dt, st);
         if (rc != VLMFW_OK) return rc;
         g = GemmArgs();
         g.a = xn;
         g.lda = D;
         g.w = w.w1;
+        g.f16 = t->f16;
         g.ldw = D;
         g.m = M;
         g.n = I;
@@ -409,6 +428,7 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.a = mid;
         g.lda = I;
         g.w = w.w2;
+        g.f16 = t->f16;
         g.ldw = I;
         g.m = M;
         g.n = D;
@@ -448,7 +468,7 @@ extern "C" int vlmfw_tower_forward_host(vlmfw_tower* t, const uint8_t* host_pixe
         if (t->host_ws) cudaFree(t->host_ws);
         t->host_ws = nullptr;
         t->host_ws_bytes = 0;
-        VLMFW_CUDA_OK(cudaMalloc(&t->host_ws, ws_bytes));
+        VLMFW_CUDA_OK(cudaMalloc(&t->host_ws, ws_bytes + 1024));  // forward() wants 1024-byte alignment (TMA tiles)
         t->host_ws_bytes = ws_bytes;
     }
     if (t->host_pooled_bytes < pooled_bytes) {
@@ -459,7 +479,8 @@ extern "C" int vlmfw_tower_forward_host(vlmfw_tower* t, const uint8_t* host_pixe
         t->host_pooled_bytes = pooled_bytes;
     }
     VLMFW_CUDA_OK(cudaMemcpyAsync(t->host_pix_dev, host_pixels, pix_bytes, cudaMemcpyHostToDevice, t->own_stream));
-    rc = vlmfw_tower_forward(t, t->host_pix_dev, VLMFW_PIX_U8_NHWC, batch, t->host_ws, t->host_ws_bytes,
+    void* ws_aligned = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(t->host_ws) + 1023) & ~uintptr_t(1023));
+    rc = vlmfw_tower_forward(t, t->host_pix_dev, VLMFW_PIX_U8_NHWC, batch, ws_aligned, t->host_ws_bytes,
                              t->host_pooled_dev, t->own_stream);
     if (rc != VLMFW_OK) return rc;
     VLMFW_CUDA_OK(cudaMemcpyAsync(host_pooled, t->host_pooled_dev, pooled_bytes, cudaMemcpyDeviceToHost, t->own_stream));
@@ -468,15 +489,17 @@ extern "C" int vlmfw_tower_forward_host(vlmfw_tower* t, const uint8_t* host_pixe
 }
 
 // ------------------------------------------------------------------------- kernel-level entry points (tests)
-extern "C" int vlmfw_gemm_bf16(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t m, int32_t n, int32_t k,
-                               const float* bias, int32_t epi, int32_t act, void* out, int32_t ldo, const float* resid,
-                               int32_t ldr, int32_t resid_mod, int32_t grp, int32_t grp_out, int32_t grp_off,
-                               int32_t block_n, void* stream) {
+extern "C" int vlmfw_gemm_tn(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t dtype, int32_t m, int32_t n,
+                             int32_t k, const float* bias, int32_t epi, int32_t act, void* out, int32_t ldo,
+                             const float* resid, int32_t ldr, int32_t resid_mod, int32_t grp, int32_t grp_out,
+                             int32_t grp_off, int32_t block_n, void* stream) {
+    VLMFW_REQUIRE(dtype == VLMFW_DT_BF16 || dtype == VLMFW_DT_F16, "gemm: dtype must be VLMFW_DT_BF16 or VLMFW_DT_F16");
     GemmArgs g;
     g.a = a;
     g.lda = lda;
     g.w = w;
     g.ldw = ldw;
+    g.f16 = dtype == VLMFW_DT_F16;
     g.m = m;
     g.n = n;
     g.k = k;
@@ -496,18 +519,21 @@ extern "C" int vlmfw_gemm_bf16(const void* a, int32_t lda, const void* w, int32_
 }
 
 extern "C" int vlmfw_layernorm(const float* x, int32_t rows, int32_t dim, const float* gamma, const float* beta,
-                               float eps, void* out, int32_t out_f32, void* stream) {
-    return launch_layernorm(x, rows, dim, gamma, beta, eps, out, out_f32 != 0, static_cast<cudaStream_t>(stream));
+                               float eps, void* out, int32_t out_dtype, void* stream) {
+    return launch_layernorm(x, rows, dim, gamma, beta, eps, out, out_dtype, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int vlmfw_attention(const void* qkv, int32_t batch, int32_t tokens, int32_t heads, int32_t head_dim,
-                               void* out, void* stream) {
-    return launch_attention(qkv, batch, tokens, heads, head_dim, out, static_cast<cudaStream_t>(stream));
+extern "C" int vlmfw_attention(const void* qkv, int32_t dtype, int32_t batch, int32_t tokens, int32_t heads,
+                               int32_t head_dim, void* out, void* stream) {
+    VLMFW_REQUIRE(dtype == VLMFW_DT_BF16 || dtype == VLMFW_DT_F16, "attention: dtype must be VLMFW_DT_BF16 or VLMFW_DT_F16");
+    return launch_attention(qkv, dtype == VLMFW_DT_F16, batch, tokens, heads, head_dim, out,
+                            static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vlmfw_im2col(const void* pixels, int32_t pix_fmt, int32_t batch, int32_t image_size, int32_t patch_size,
-                            const float* mean, const float* std, void* out, int32_t kpad, void* stream) {
-    return launch_im2col(pixels, pix_fmt, batch, image_size, patch_size, mean, std, out, kpad,
+                            const float* mean, const float* std, void* out, int32_t kpad, int32_t out_dtype,
+                            void* stream) {
+    return launch_im2col(pixels, pix_fmt, batch, image_size, patch_size, mean, std, out, kpad, out_dtype == VLMFW_DT_F16,
                          static_cast<cudaStream_t>(stream));
 }
 
@@ -516,6 +542,8 @@ extern "C" int vlmfw_pool(const float* h, int32_t batch, int32_t tokens, int32_t
     return launch_pool(h, batch, tokens, dim, pool, gamma, beta, eps, pooled_out, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int vlmfw_pack_bf16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, void* stream) {
-    return launch_pack_bf16(src, rows, cols, dst, dst_ld, static_cast<cudaStream_t>(stream));
+extern "C" int vlmfw_pack_16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, int32_t dtype,
+                             void* stream) {
+    VLMFW_REQUIRE(dtype == VLMFW_DT_BF16 || dtype == VLMFW_DT_F16, "pack_16: dtype must be VLMFW_DT_BF16 or VLMFW_DT_F16");
+    return launch_pack_16(src, rows, cols, dst, dst_ld, dtype == VLMFW_DT_F16, static_cast<cudaStream_t>(stream));
 }

@@ -35,24 +35,38 @@ def require_cuda(device) -> torch.device:
 
 
 class TowerEngine:
-    """One vision tower with packed bf16 weights resident in HBM, replicated per GPU (data parallel)."""
+    """One vision tower with packed 16-bit weights resident in HBM, replicated per GPU (data parallel).
 
-    def __init__(self, spec: TowerSpec, device="cuda"):
+    ``compute_dtype``: "f16" (default; falls back to bf16 automatically when a weight exceeds the fp16 range), or
+    "bf16" to force bf16 operands. See ``VLMFW_CDT_*`` in include/vlmfw_b200.h for why fp16 is the default.
+    """
+
+    def __init__(self, spec: TowerSpec, device="cuda", compute_dtype: str = "f16"):
         self.spec = spec
         self.device = require_cuda(device)
         self._lib = _lib.load()
+        if compute_dtype not in ("f16", "bf16"):
+            raise ValueError("compute_dtype must be 'f16' or 'bf16'")
+        self.compute_dtype = compute_dtype
+        self._h = None
+        self._create()
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_batch = 0
+        self._graphs: Dict[tuple, tuple] = {}
+
+    def _create(self) -> None:
+        spec = self.spec
+        self.close()
         cfg = _lib.TowerCfg(
             arch=spec.arch, image_size=spec.image_size, patch_size=spec.patch_size, hidden=spec.hidden,
             heads=spec.heads, mlp=spec.mlp, layers=spec.layers, has_cls=int(spec.has_cls),
             has_pre_ln=int(spec.has_pre_ln), conv_bias=int(spec.conv_bias), act=spec.act, pool=spec.pool,
-            ln_eps=spec.ln_eps, pix_mean=(C.c_float * 3)(*spec.pix_mean), pix_std=(C.c_float * 3)(*spec.pix_std))
+            ln_eps=spec.ln_eps, pix_mean=(C.c_float * 3)(*spec.pix_mean), pix_std=(C.c_float * 3)(*spec.pix_std),
+            compute_dtype=_lib.CDT_F16 if self.compute_dtype == "f16" else _lib.CDT_BF16)
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.vlmfw_tower_create(C.byref(cfg), C.byref(handle)))
         self._h = handle
-        self._ws: Optional[torch.Tensor] = None
-        self._ws_batch = 0
-        self._graphs: Dict[tuple, tuple] = {}
 
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:
@@ -68,7 +82,18 @@ class TowerEngine:
 
     # ------------------------------------------------------------------ weights
     def load_canonical(self, tensors: Mapping[str, torch.Tensor]) -> None:
-        """Upload ``{canonical name: tensor}`` (any device / float dtype); matrices are repacked to bf16 on the GPU."""
+        """Upload ``{canonical name: tensor}`` (any device / float dtype); matrices are repacked to 16 bits on the GPU.
+        A weight outside the fp16 range (VLMFW_E_RANGE) rebuilds the tower in bf16 and loads again."""
+        try:
+            self._load_canonical(tensors)
+        except _lib.VlmfwError as err:
+            if err.code != _lib.E_RANGE or self.compute_dtype == "bf16":
+                raise
+            self.compute_dtype = "bf16"
+            self._create()
+            self._load_canonical(tensors)
+
+    def _load_canonical(self, tensors: Mapping[str, torch.Tensor]) -> None:
         with torch.cuda.device(self.device):
             st = _stream_ptr(self.device)
             for name in canonical_names(self.spec):

@@ -28,25 +28,34 @@ def _need(t: torch.Tensor, dtype, name: str) -> None:
         raise ValueError(f"{name} must be contiguous")
 
 
-def pack_bf16(src: torch.Tensor, ld: Optional[int] = None) -> torch.Tensor:
-    """fp32 [rows, cols] -> bf16 [rows, ld] (zero padded), round-to-nearest-even like torch's ``.to(bfloat16)``."""
+def _dt(t: torch.Tensor, name: str) -> int:
+    if t.dtype == torch.bfloat16:
+        return _lib.DT_BF16
+    if t.dtype == torch.float16:
+        return _lib.DT_F16
+    raise TypeError(f"{name} must be bfloat16 or float16, got {t.dtype}")
+
+
+def pack_16(src: torch.Tensor, ld: Optional[int] = None, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 / fp16 [rows, ld] (zero padded), round-to-nearest-even like torch's ``.to(dtype)``."""
     _need(src, torch.float32, "src")
     rows, cols = src.shape
     ld = cols if ld is None else ld
-    dst = torch.empty(rows, ld, dtype=torch.bfloat16, device=src.device)
+    dst = torch.empty(rows, ld, dtype=dtype, device=src.device)
     with torch.cuda.device(src.device):
-        _lib.check(_lib.load().vlmfw_pack_bf16(src.data_ptr(), rows, cols, dst.data_ptr(), ld, _st(src)))
+        _lib.check(_lib.load().vlmfw_pack_16(src.data_ptr(), rows, cols, dst.data_ptr(), ld, _dt(dst, "dst"), _st(src)))
     return dst
 
 
-def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
+def gemm_tn(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
               resid: Optional[torch.Tensor] = None, resid_mod: int = 0, out: Optional[torch.Tensor] = None,
               grp: int = 0, grp_out: int = 0, grp_off: int = 0, out_rows: Optional[int] = None,
               block_n: int = 0) -> torch.Tensor:
-    """``epilogue(a[M,K] @ w[N,K]^T)`` on tcgen05. Without ``resid``: bf16 ``act(acc + bias)``; with ``resid``
-    (fp32 [*, N]): fp32 ``acc + bias + resid[row % resid_mod]``."""
-    _need(a, torch.bfloat16, "a")
-    _need(w, torch.bfloat16, "w")
+    """``epilogue(a[M,K] @ w[N,K]^T)`` on tcgen05; a and w share one 16-bit dtype (bf16 or fp16). Without ``resid``:
+    ``act(acc + bias)`` in that dtype; with ``resid`` (fp32 [*, N]): fp32 ``acc + bias + resid[row % resid_mod]``."""
+    _need(a, a.dtype, "a")
+    _need(w, a.dtype, "w")
+    dt = _dt(a, "a")
     m, k = a.shape
     n, k2 = w.shape
     if k != k2:
@@ -63,57 +72,59 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
     else:
         epi = EPI_BIAS_BF16
         if out is None:
-            out = torch.empty(rows, n, dtype=torch.bfloat16, device=a.device)
-        _need(out, torch.bfloat16, "out")
+            out = torch.empty(rows, n, dtype=a.dtype, device=a.device)
+        _need(out, a.dtype, "out")
     with torch.cuda.device(a.device):
-        _lib.check(_lib.load().vlmfw_gemm_bf16(
-            a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), m, n, k,
+        _lib.check(_lib.load().vlmfw_gemm_tn(
+            a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), dt, m, n, k,
             None if bias is None else bias.data_ptr(), epi, act, out.data_ptr(), out.stride(0),
             None if resid is None else resid.data_ptr(), 0 if resid is None else resid.stride(0), resid_mod,
             grp, grp_out, grp_off, block_n, _st(a)))
     return out
 
 
-def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_f32: bool = False,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              dtype: torch.dtype = torch.float16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need(x, torch.float32, "x")
     _need(gamma, torch.float32, "gamma")
     _need(beta, torch.float32, "beta")
     rows, dim = x.shape
     if out is None:
-        out = torch.empty(rows, dim, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+        out = torch.empty(rows, dim, dtype=dtype, device=x.device)
+    odt = _lib.DT_F32 if out.dtype == torch.float32 else _dt(out, "out")
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().vlmfw_layernorm(x.data_ptr(), rows, dim, gamma.data_ptr(), beta.data_ptr(), eps,
-                                               out.data_ptr(), int(out_f32), _st(x)))
+                                               out.data_ptr(), odt, _st(x)))
     return out
 
 
 def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: int) -> torch.Tensor:
-    """qkv bf16 [B*S, 3*H*dh] (q | k | v thirds) -> softmax(QK^T/sqrt(dh)) V as bf16 [B*S, H*dh]."""
-    _need(qkv, torch.bfloat16, "qkv")
+    """qkv 16-bit [B*S, 3*H*dh] (q | k | v thirds) -> softmax(QK^T/sqrt(dh)) V in the same dtype [B*S, H*dh]."""
+    _need(qkv, qkv.dtype, "qkv")
+    dt = _dt(qkv, "qkv")
     d = heads * head_dim
     if tuple(qkv.shape) != (batch * tokens, 3 * d):
         raise ValueError(f"qkv must be [{batch * tokens}, {3 * d}], got {tuple(qkv.shape)}")
-    out = torch.empty(batch * tokens, d, dtype=torch.bfloat16, device=qkv.device)
+    out = torch.empty(batch * tokens, d, dtype=qkv.dtype, device=qkv.device)
     with torch.cuda.device(qkv.device):
-        _lib.check(_lib.load().vlmfw_attention(qkv.data_ptr(), batch, tokens, heads, head_dim, out.data_ptr(),
+        _lib.check(_lib.load().vlmfw_attention(qkv.data_ptr(), dt, batch, tokens, heads, head_dim, out.data_ptr(),
                                                _st(qkv)))
     return out
 
 
 def im2col(pixels: torch.Tensor, image_size: int, patch: int, kpad: int, mean: Sequence[float] = (0, 0, 0),
-           std: Sequence[float] = (1, 1, 1)) -> torch.Tensor:
+           std: Sequence[float] = (1, 1, 1), dtype: torch.dtype = torch.float16) -> torch.Tensor:
     if not pixels.is_cuda or not pixels.is_contiguous():
         raise RuntimeError("pixels must be a contiguous CUDA tensor")
     fmt = 0 if pixels.dtype == torch.uint8 else 1
     b = pixels.shape[0]
     g = image_size // patch
-    out = torch.empty(b * g * g, kpad, dtype=torch.bfloat16, device=pixels.device)
+    out = torch.empty(b * g * g, kpad, dtype=dtype, device=pixels.device)
     m3 = (C.c_float * 3)(*mean)
     s3 = (C.c_float * 3)(*std)
     with torch.cuda.device(pixels.device):
         _lib.check(_lib.load().vlmfw_im2col(pixels.data_ptr(), fmt, b, image_size, patch, m3, s3, out.data_ptr(), kpad,
-                                            _st(pixels)))
+                                            _dt(out, "out"), _st(pixels)))
     return out
 
 

@@ -10,6 +10,7 @@ bf16 weights run through ``libvlmfw_b200.so``. ``self.vision_model`` stays a reg
 """
 from __future__ import annotations
 
+import os
 import re
 from abc import ABC, abstractmethod
 from typing import Callable, Dict, List, Optional, Sequence, Union
@@ -58,8 +59,11 @@ class B200VisionBackbone(VisionBackbone):
     ARCH: int = -1
     PROMPT: Optional[str] = None  # the dummy ``text=`` the reference passes to its processor
 
-    def __init__(self, processor, vision_model, output_dim, device, spec: Optional[TowerSpec] = None):
+    def __init__(self, processor, vision_model, output_dim, device, spec: Optional[TowerSpec] = None,
+                 compute_dtype: Optional[str] = None):
         super().__init__(processor, vision_model, output_dim, device)
+        # "f16" (default) or "bf16": 16-bit format of the tensor-core operands, see VLMFW_CDT_* in vlmfw_b200.h
+        self.compute_dtype = compute_dtype or os.environ.get("VLMFW_COMPUTE_DTYPE", "f16")
         if spec is None:
             cfg = getattr(vision_model, "config", None)
             if cfg is None:
@@ -96,7 +100,7 @@ class B200VisionBackbone(VisionBackbone):
         eng = self._engines.get(key)
         if eng is None or getattr(eng, "_version", -1) != self._weights_version:
             spec = self.spec.with_pool(pool)
-            eng = TowerEngine(spec, dev)
+            eng = TowerEngine(spec, dev, compute_dtype=self.compute_dtype)
             eng.load_hf_state_dict(self.vision_model.state_dict())
             eng._version = self._weights_version
             self._engines[key] = eng
@@ -245,7 +249,8 @@ class BLIP2Backbone(B200VisionBackbone):
 BACKBONES = {ARCH_SIGLIP: PaliGemmaBackbone, ARCH_CLIP: LLaVABackbone, ARCH_EVA: BLIP2Backbone}
 
 
-def backbone_from_spec(spec: TowerSpec, state_dict=None, device="cuda", processor=None, seed: int = 0):
+def backbone_from_spec(spec: TowerSpec, state_dict=None, device="cuda", processor=None, seed: int = 0,
+                       compute_dtype: Optional[str] = None):
     """Offline constructor (tests, bench): HF vision module from config + given (or seeded) weights, wrapped in the
     matching B200 adapter. No network, no ``from_pretrained``."""
     import transformers as tf
@@ -270,4 +275,5 @@ def backbone_from_spec(spec: TowerSpec, state_dict=None, device="cuda", processo
             buf.copy_(torch.arange(buf.shape[-1]).expand(buf.shape))
     module.load_state_dict(sd, strict=True)
     module.eval()
-    return BACKBONES[spec.arch](processor, module, spec.hidden, torch.device(device), spec=spec)
+    return BACKBONES[spec.arch](processor, module, spec.hidden, torch.device(device), spec=spec,
+                                compute_dtype=compute_dtype)
