@@ -129,6 +129,39 @@ def test_attention(cuda_device, batch, tokens, heads, dh, dtype):
     torch.testing.assert_close(out.float(), ref, rtol=tol, atol=tol)
 
 
+def _attn_ref(qkv, batch, tokens, heads, dh):
+    d = heads * dh
+    q, k, v = (t.view(batch, tokens, heads, dh).transpose(1, 2) for t in qkv.float().split(d, dim=-1))
+    att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), dim=-1)
+    return (att @ v).transpose(1, 2).reshape(batch * tokens, d)
+
+
+@pytest.mark.parametrize("batch,tokens,heads,dh", [(24, 256, 16, 72), (7, 577, 16, 64), (9, 257, 16, 88)])
+def test_attention_persistent_many_items(cuda_device, batch, tokens, heads, dh):
+    """More work items than SMs: every CTA of the persistent tcgen05 kernel loops over several (image, head, query-pair)
+    items, so barrier phases, TMEM reuse and the K/V ring wrap around many times."""
+    qkv = _rand((batch * tokens, 3 * heads * dh), 31, 1.2).to(torch.float16)
+    out = ops.attention(qkv, batch, tokens, heads, dh)
+    torch.testing.assert_close(out.float(), _attn_ref(qkv, batch, tokens, heads, dh), rtol=3e-3, atol=3e-3)
+
+
+@pytest.mark.parametrize("tokens,dh", [(256, 72), (577, 64), (257, 88)])
+def test_attention_running_max_rescale(cuda_device, tokens, dh):
+    """Scores that grow along the key axis force the running max up by more than 2^8 between key blocks, i.e. the path
+    that rescales the O accumulator inside TMEM."""
+    batch, heads = 2, 4
+    d = heads * dh
+    qkv = _rand((batch * tokens, 3 * d), 32, 1.0)
+    ramp = torch.linspace(0.2, 6.0, tokens, device="cuda").repeat(batch)[:, None]
+    qkv[:, d:2 * d] *= ramp  # keys of later tokens are much larger
+    qkv[:, :d] *= 2.0
+    qkv = qkv.to(torch.float16)
+    out = ops.attention(qkv, batch, tokens, heads, dh)
+    ref = _attn_ref(qkv, batch, tokens, heads, dh)
+    assert torch.isfinite(out.float()).all()
+    torch.testing.assert_close(out.float(), ref, rtol=5e-3, atol=5e-3)
+
+
 @pytest.mark.parametrize("fmt", ["u8", "f32"])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_im2col(cuda_device, fmt, dtype):

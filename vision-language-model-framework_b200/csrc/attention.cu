@@ -11,6 +11,8 @@
 // exp2 and warp-shuffle quad reductions; P is re-used from registers as the A operand of P·V.
 // head_dim 72 / 88 are zero-padded to 80 / 96 in shared memory only (K of QK^T must be a multiple of 16).
 // S in {256, 257, 577}: the ragged last key tile is zero-filled and masked to -inf.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -246,6 +248,16 @@ int launch_attention(const void* qkv, bool f16, int batch, int tokens, int heads
     VLMFW_REQUIRE(batch <= 65535 && heads <= 65535, "attention: grid too large");
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
+    // head_dim 64 / 72 / 88 run on the tcgen05 kernel; anything else (and VLMFW_ATTN_LEGACY=1, for A/B timing) on the
+    // generic mma.sync kernel below
+    static const bool legacy = []() {
+        const char* e = getenv("VLMFW_ATTN_LEGACY");
+        return e != nullptr && e[0] == '1';
+    }();
+    if (!legacy) {
+        rc = launch_attention_tc(qkv, f16, batch, tokens, heads, head_dim, out, stream);
+        if (rc <= 0) return rc;
+    }
     if (f16) {
         if (head_dim <= 64) return launch_att<64, true>(qkv, batch, tokens, heads, head_dim, out, stream);
         if (head_dim <= 80) return launch_att<80, true>(qkv, batch, tokens, heads, head_dim, out, stream);

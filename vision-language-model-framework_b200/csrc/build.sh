@@ -8,7 +8,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompil
        --expt-relaxed-constexpr -Xptxas -v)
 mkdir -p "${HERE}/build"
 pids=()
-for f in gemm_tcgen05 layernorm embed attention probe tower; do
+for f in gemm_tcgen05 layernorm embed attention attention_tc probe tower; do
   ( "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${HERE}/build/${f}.o" > "${HERE}/build/${f}.log" 2>&1 ) &
   pids+=($!)
 done

@@ -1,5 +1,6 @@
 // Shared host-side declarations of the kernel launchers (one translation unit per kernel family).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -57,6 +58,11 @@ struct GemmArgs {
     bool f16 = false;  // 16-bit format of A, W and the 16-bit output: false = bf16, true = fp16 (A and W must agree)
 };
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda). dims[0] / box[0] = innermost.
+// strides_bytes has rank-1 entries (dims 1..rank-1). swizzle_bytes in {0, 32, 64, 128}.
+int encode_tensor_map(CUtensorMap* out, bool f16, int rank, const void* ptr, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+
 int device_check();
 int num_sms();
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
@@ -64,6 +70,9 @@ int launch_layernorm(const float* x, int rows, int dim, const float* gamma, cons
                      int out_dtype, cudaStream_t stream);
 int launch_attention(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out,
                      cudaStream_t stream);
+// tcgen05 attention (attention_tc.cu): 0 = launched, 1 = shape not covered (use launch_attention's generic kernel), <0 = error
+int launch_attention_tc(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out,
+                        cudaStream_t stream);
 int launch_im2col(const void* pixels, int pix_fmt, int batch, int image_size, int patch, const float* mean3,
                   const float* std3, void* out, int kpad, bool out_f16, cudaStream_t stream);
 int launch_fill_cls(const float* cls_pos0, float* h, int batch, int tokens, int dim, cudaStream_t stream);

@@ -447,6 +447,35 @@ int pick_block_n(int n) {
 
 }  // namespace
 
+int encode_tensor_map(CUtensorMap* out, bool f16, int rank, const void* ptr, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return VLMFW_E_CUDA;
+    }
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t bx[5], estride[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        estride[i] = 1;
+        if (i > 0) gstride[i - 1] = strides_bytes[i - 1];
+    }
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                        : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = fn(out, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+                    const_cast<void*>(ptr), gdim, gstride, bx, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(rank %d) failed (CUresult %d)", rank, static_cast<int>(r));
+        return VLMFW_E_CUDA;
+    }
+    return VLMFW_OK;
+}
+
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     VLMFW_REQUIRE(g.a && g.w && g.out, "gemm: null operand");
     VLMFW_REQUIRE(g.m > 0 && g.n > 0 && g.k > 0, "gemm: bad shape m=%d n=%d k=%d", g.m, g.n, g.k);
