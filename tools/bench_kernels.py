@@ -71,8 +71,10 @@ def main():
         med, best = timeit(lambda: ops.layernorm(x, g, b, 1e-6, out=out))
         byts = m * d * 6
         print(json.dumps({"kernel": "layernorm", "rows": m, "dim": d, "ms": round(med, 4), "gbs": round(byts / med / 1e6, 1)}), flush=True)
-    if not args.only or "att" in args.only:
+    if not args.only or args.only.endswith("att"):
         for name, s, hd, dh in [("siglip.att", 256, 16, 72), ("clip.att", 577, 16, 64), ("eva.att", 257, 16, 88)]:
+            if args.only and args.only not in name and args.only != "att":
+                continue
             bsz = max(1, m // s)
             qkv = (torch.randn(bsz * s, 3 * hd * dh, device=dev)).to(DT)
             med, best = timeit(lambda: ops.attention(qkv, bsz, s, hd, dh))

@@ -2,12 +2,12 @@
 // Restates hf integrations/sdpa_attention.py:92 as called from modeling_siglip.py:285-309, modeling_clip.py:310-334 and
 // modeling_blip_2.py:328-351 — same contract and layouts as attention.cu (qkv [B*S, 3D] in, ctx [B*S, D] out).
 //
-// Persistent, warp-specialised, one CTA per SM (320 threads); a work item = (image, head, PAIR of 128-query blocks):
+// Persistent, warp-specialised, one CTA per SM (384 threads); a work item = (image, head, PAIR of 128-query blocks):
 //   warp 0       TMA loader  — 5-D tensor map over qkv (head_dim, head, q|k|v, token, image): out-of-range head_dim
 //                              columns and tokens past S arrive as zeros, so head_dim 72 / 88 need no padding in HBM
 //   warp 1       MMA issuer  — S_qb = Q_qb K_j^T (tcgen05.mma 128x128xdh, accumulator in TMEM), O_qb += P_qb V_j
 //                              (128 x dh x 128, V read MN-major straight from the token-major tile, no transpose)
-//   warps 2..5   softmax of query block 0, warps 6..9 of query block 1 (one thread = one query row = one TMEM lane):
+//   warps 4..7   softmax of query block 0, warps 8..11 of query block 1 (one thread = one query row = one TMEM lane):
 //                tcgen05.ld the 128 scores, row max / exp2 / row sum in registers with no shuffles, P -> fp16/bf16 ->
 //                128B-swizzled smem as the A operand of the P·V MMA. The two blocks ping-pong so the tensor pipe works
 //                on one while the SFUs exponentiate the other; both share every K/V tile.
@@ -15,6 +15,7 @@
 // same reference max divides numerator and denominator); then O is rescaled in TMEM by the softmax warps.
 // head_dim = 64 + tail (0 / 8->16 / 24->32 columns): the tail lives in its own narrow 32B / 64B-swizzled tile and is
 // one extra K-step of Q·K^T and one extra narrow-N MMA of P·V.
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -24,7 +25,7 @@
 namespace vlmfw {
 namespace {
 
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 384;  // 3 warpgroups: {loader, MMA, 2 idle} + softmax(q block 0) + softmax(q block 1)
 constexpr int BLK = 128;  // query rows per block (= TMEM lanes) and keys per block
 
 template <int DH>
@@ -49,6 +50,7 @@ struct TcParams {
     int num_items;  // B * H * nqp
     float scale_log2;
     int f16;
+    int dbg;  // VLMFW_ATTN_DBG bit mask (bottleneck experiments only): 1 skip exp+P store, 2 skip P·V MMAs, 4 skip S MMAs, 8 skip max
 };
 
 // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512)
@@ -110,6 +112,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
     const uint32_t tmem_base = *tmem_slot;
     const int J = p.J;
 
+    // Register rebalancing (setmaxnreg works per warpgroup, inside the 384 x 168 registers the CTA was launched with:
+    // 128 x 56 + 256 x 224 = 64512): the producer warpgroup needs a handful of registers, a
+    // softmax thread keeps one full 128-score row (+ the O row in the epilogue) in registers.
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------ TMA loader
         if (lane == 0) {
@@ -118,9 +125,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
                 const int qp = item % p.nqp;
                 const int h = (item / p.nqp) % p.H;
                 const int b = item / (p.nqp * p.H);
+                const int nqb = ((qp * 2 + 1) * BLK < p.S) ? 2 : 1;  // the odd last query block has no partner
                 mbar_wait(q_empty, (it & 1) ^ 1);
-                mbar_arrive_expect_tx(q_full, 2 * C::TILE_BYTES);
-                for (int qb = 0; qb < 2; ++qb) {
+                mbar_arrive_expect_tx(q_full, nqb * C::TILE_BYTES);
+                for (int qb = 0; qb < nqb; ++qb) {
                     const int tok0 = (qp * 2 + qb) * BLK;
                     tma_load_5d(sQ + qb * C::TILE_BYTES, &map_main, q_full, 0, h, 0, tok0, b);
                     if (C::TAIL) tma_load_5d(sQ + qb * C::TILE_BYTES + C::MAIN_BYTES, &map_tail, q_full, 64, h, 0, tok0, b);
@@ -143,15 +151,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
         // ------------------------------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const bool f16 = p.f16 != 0;
-            const uint32_t idesc_s = umma_idesc_16(BLK, BLK, f16, f16);
             const uint32_t idesc_pv = umma_idesc_16_bmn(BLK, 64, f16);
             const uint32_t idesc_pvt = umma_idesc_16_bmn(BLK, C::TAIL ? C::TAIL : 16, f16);
             const uint32_t q_u32 = smem_u32(sQ), k_u32 = smem_u32(sK), v_u32 = smem_u32(sV), p_u32 = smem_u32(sP);
 
-            auto issue_s = [&](int qb, int st) {
+            // kcols = keys of this block rounded up to 32: the ragged last block (S = 257 -> 1 key, 577 -> 65) runs a
+            // narrower S MMA, fewer exponentials and fewer P·V K-steps instead of a full 128-key block
+            auto issue_s = [&](int qb, int st, int kcols) {
                 const uint32_t d = tmem_base + TM_S + qb * TM_STRIDE;
                 const uint32_t a0 = q_u32 + qb * C::TILE_BYTES, b0 = k_u32 + st * C::TILE_BYTES;
                 const uint64_t ad = umma_desc_sw128(a0), bd = umma_desc_sw128(b0);
+                const uint32_t idesc_s = umma_idesc_16(BLK, kcols, f16, f16);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(d, ad + 2 * ks, bd + 2 * ks, idesc_s, ks > 0 ? 1u : 0u);
                 if (C::TAIL) {
@@ -161,11 +171,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
                     for (int ks = 0; ks < C::TAIL / 16; ++ks) umma_bf16_ss(d, at + 2 * ks, bt + 2 * ks, idesc_s, 1u);
                 }
             };
-            auto issue_pv = [&](int qb, int st, bool acc) {
+            auto issue_pv = [&](int qb, int st, bool acc, int kcols) {
                 const uint32_t d = tmem_base + TM_O + qb * TM_STRIDE;
                 const uint32_t a0 = p_u32 + qb * C::P_BYTES, b0 = v_u32 + st * C::TILE_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {  // 16 keys per step
+                const int ksteps = kcols >> 4;  // 16 keys per step
+#pragma unroll 1
+                for (int ks = 0; ks < ksteps; ++ks) {
                     const uint64_t ad = umma_desc_sw128(a0 + (ks >> 2) * 16384) + 2 * (ks & 3);
                     // V main tile: token-major rows of 128 B (64 head_dim columns) = MN-major SWIZZLE_128B operand;
                     // 8-key groups are 1024 B apart, one K-step (16 keys) = 2048 B
@@ -178,59 +189,68 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
                     }
                 }
             };
+            auto kcols_of = [&](int j) {
+                const int valid = p.S - j * BLK;
+                return valid >= BLK ? BLK : ((valid + 31) >> 5) << 5;
+            };
+            auto nqb_of = [&](int k) {
+                const int qp = (static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x)) % p.nqp;
+                return ((qp * 2 + 1) * BLK < p.S) ? 2 : 1;
+            };
 
-            int it = 0, g = 0;
-            uint32_t n[2] = {0, 0};  // S blocks issued per query block (global count) == P·V blocks issued + pending
-            uint32_t npv[2] = {0, 0};
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-                mbar_wait(q_full, it & 1);
-                {
-                    const int st = g & 1;
-                    mbar_wait(&k_full[st], (g >> 1) & 1);
+            // The key blocks of all of this CTA's items form one stream t = 0 .. T-1 (item t / J, block t % J): the
+            // scores of block t+1 are issued before P·V of block t — across item boundaries too — so the softmax warps
+            // always find their next S tile ready.
+            const int n_local = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                static_cast<int>(gridDim.x);
+            const int T = n_local * J;
+            uint32_t n[2] = {0, 0};    // S tiles issued per query block
+            uint32_t npv[2] = {0, 0};  // P·V blocks issued per query block
+            uint32_t itq[2] = {0, 0};  // items started per query block (o_empty phase)
+            auto issue_s_stage = [&](int t) {
+                const int k = t / J, j = t - k * J, st = t & 1;
+                if (j == 0) mbar_wait(q_full, k & 1);
+                mbar_wait(&k_full[st], (t >> 1) & 1);
+                const int nq = nqb_of(k), kcols = kcols_of(j);
+                for (int qb = 0; qb < nq; ++qb) {
+                    mbar_wait(&s_empty[qb], (n[qb] & 1) ^ 1);
                     tc_fence_after();
-                    for (int qb = 0; qb < 2; ++qb) {
-                        mbar_wait(&s_empty[qb], (n[qb] & 1) ^ 1);
-                        tc_fence_after();
-                        issue_s(qb, st);
-                        umma_commit(&s_full[qb]);
-                        ++n[qb];
-                    }
-                    umma_commit(&k_empty[st]);
-                    if (J == 1) umma_commit(q_empty);
+                    if (!(p.dbg & 4)) issue_s(qb, st, kcols);
+                    umma_commit(&s_full[qb]);
+                    ++n[qb];
                 }
-                for (int j = 0; j < J; ++j) {
-                    const int gj = g + j;
-                    const int stj = gj & 1;
-                    for (int qb = 0; qb < 2; ++qb) {
-                        if (j + 1 < J) {  // next block's scores first: they do not depend on O and keep the SFUs fed
-                            const int g1 = gj + 1, st1 = g1 & 1;
-                            if (qb == 0) mbar_wait(&k_full[st1], (g1 >> 1) & 1);
-                            mbar_wait(&s_empty[qb], (n[qb] & 1) ^ 1);
-                            tc_fence_after();
-                            issue_s(qb, st1);
-                            umma_commit(&s_full[qb]);
-                            ++n[qb];
-                            if (qb == 1) {
-                                umma_commit(&k_empty[st1]);
-                                if (j + 1 == J - 1) umma_commit(q_empty);
-                            }
-                        }
-                        mbar_wait(&p_full[qb], npv[qb] & 1);
-                        if (j == 0) mbar_wait(&o_empty[qb], (it & 1) ^ 1);
-                        if (qb == 0) mbar_wait(&v_full[stj], (gj >> 1) & 1);
-                        tc_fence_after();
-                        issue_pv(qb, stj, j > 0);
-                        umma_commit(&pv_done[qb]);
-                        ++npv[qb];
+                umma_commit(&k_empty[st]);
+                if (j == J - 1) umma_commit(q_empty);
+            };
+            if (T > 0) issue_s_stage(0);
+            for (int t = 0; t < T; ++t) {
+                const int k = t / J, j = t - k * J, st = t & 1;
+                // next block's scores go first, except across an item boundary: there they would wait for the next
+                // item's Q tile and hold up this item's last P·V (and with it the epilogue)
+                const bool s_first = j + 1 < J;
+                if (s_first && t + 1 < T) issue_s_stage(t + 1);
+                const int nq = nqb_of(k), kcols = kcols_of(j);
+                mbar_wait(&v_full[st], (t >> 1) & 1);
+                for (int qb = 0; qb < nq; ++qb) {
+                    mbar_wait(&p_full[qb], npv[qb] & 1);
+                    if (j == 0) {
+                        mbar_wait(&o_empty[qb], (itq[qb] & 1) ^ 1);
+                        ++itq[qb];
                     }
-                    umma_commit(&v_empty[stj]);
+                    tc_fence_after();
+                    if (!(p.dbg & 2)) issue_pv(qb, st, j > 0, kcols);
+                    umma_commit(&pv_done[qb]);
+                    ++npv[qb];
                 }
-                g += J;
+                umma_commit(&v_empty[st]);
+                if (!s_first && t + 1 < T) issue_s_stage(t + 1);
             }
         }
+    }
     } else {
         // ------------------------------------------------------------------------------------------ softmax warps
-        const int qb = (warp - 2) >> 2;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int qb = (warp - 4) >> 2;
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -244,36 +264,53 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
             const int qp = item % p.nqp;
             const int h = (item / p.nqp) % p.H;
             const int b = item / (p.nqp * p.H);
+            if ((qp * 2 + qb) * BLK >= p.S) continue;  // no such query block (loader and MMA warp skip it too)
             const int tok = (qp * 2 + qb) * BLK + row;
+            // warps whose 32 rows all lie past the last token keep the barrier protocol but skip the arithmetic
+            const bool warp_live = (qp * 2 + qb) * BLK + quarter * 32 < p.S;
             float m = 0.f, l = 0.f;
             for (int j = 0; j < J; ++j, ++n) {
+                const int valid = p.S - j * BLK;
+                const int nch = valid >= BLK ? 4 : (valid + 31) >> 5;  // 32-key chunks of this block
                 mbar_wait(&s_full[qb], n & 1);
                 tc_fence_after();
                 uint32_t v[BLK];
+                if (warp_live) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
-                tmem_ld_wait();
+                    for (int c = 0; c < 4; ++c)
+                        if (c < nch) tmem_ld_32x32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+                    tmem_ld_wait();
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_empty[qb]);
-                const int valid = p.S - j * BLK;
-                if (valid < BLK) {
-#pragma unroll
-                    for (int i = 0; i < BLK; ++i)
-                        if (i >= valid) v[i] = 0xFF800000u;  // -inf: key past the end of the image
-                }
-                float mx = __uint_as_float(v[0]);
-#pragma unroll
-                for (int i = 1; i < BLK; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-                const float tmax = mx * p.scale_log2;
                 float factor = 1.f;
                 bool need = false;
-                if (j == 0) {
-                    m = tmax;
-                } else if (tmax > m + 8.f) {
-                    factor = ex2_approx(m - tmax);
-                    m = tmax;
-                    need = true;
+                if (warp_live && !(p.dbg & 8)) {
+                    if (valid < nch * 32) {
+#pragma unroll
+                        for (int i = 0; i < BLK; ++i)
+                            if (i >= valid) v[i] = 0xFF800000u;  // -inf: key past the end of the image
+                    }
+                    // four independent max chains (one per 32-key chunk) instead of one 128-long dependent chain
+                    float mxc[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        mxc[c] = __uint_as_float(v[0]);
+                        if (c < nch) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) mxc[c] = fmaxf(mxc[c], __uint_as_float(v[c * 32 + i]));
+                        }
+                    }
+                    const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
+                    const float tmax = mx * p.scale_log2;
+                    if (j == 0) {
+                        m = tmax;
+                    } else if (tmax > m + 8.f) {
+                        factor = ex2_approx(m - tmax);
+                        m = tmax;
+                        need = true;
+                    }
                 }
                 if (j > 0) {
                     // P·V of the previous block has finished: P (smem) and O (TMEM) may be touched again
@@ -293,30 +330,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
                         l *= factor;
                     }
                 }
-                float sum = 0.f;
+                if (warp_live && !(p.dbg & 1)) {
+                    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+                    const float neg_m = -m, sc = p.scale_log2;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 keys = 16 bytes of P
-                    float e[8];
+                    for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 keys = 16 bytes of P
+                        if ((c >> 2) < nch) {
+                            // in place, 8 independent FFMA then 8 independent MUFU.EX2 (no shared temporary: the SFU
+                            // pipe is the bound of this kernel, the chain FFMA -> EX2 -> FFMA must not serialise)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        e[i] = ex2_approx(fmaf(__uint_as_float(v[c * 8 + i]), p.scale_log2, -m));
-                        sum += e[i];
+                            for (int i = 0; i < 8; ++i)
+                                v[c * 8 + i] = __float_as_uint(fmaf(__uint_as_float(v[c * 8 + i]), sc, neg_m));
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                v[c * 8 + i] = __float_as_uint(ex2_approx(__uint_as_float(v[c * 8 + i])));
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) sum[i & 3] += __uint_as_float(v[c * 8 + i]);
+                            uint32_t w[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float e0 = __uint_as_float(v[c * 8 + 2 * i]), e1 = __uint_as_float(v[c * 8 + 2 * i + 1]);
+                                w[i] = f16 ? pack_f16x2(e0, e1) : pack_bf16x2(e0, e1);
+                            }
+                            // K-major SWIZZLE_128B A tile: key group (c >> 3) is a [128 x 128 B] slab, 16-byte chunk
+                            // (c & 7) of this row sits at chunk index (c & 7) ^ (row & 7)
+                            const uint32_t dst = prow_u32 + (c >> 3) * 16384 + ((((c & 7) ^ (row & 7))) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]),
+                                         "r"(w[2]), "r"(w[3])
+                                         : "memory");
+                        }
                     }
-                    uint32_t w0, w1, w2, w3;
-                    if (f16) {
-                        w0 = pack_f16x2(e[0], e[1]); w1 = pack_f16x2(e[2], e[3]);
-                        w2 = pack_f16x2(e[4], e[5]); w3 = pack_f16x2(e[6], e[7]);
-                    } else {
-                        w0 = pack_bf16x2(e[0], e[1]); w1 = pack_bf16x2(e[2], e[3]);
-                        w2 = pack_bf16x2(e[4], e[5]); w3 = pack_bf16x2(e[6], e[7]);
-                    }
-                    // K-major SWIZZLE_128B A tile: key group (c >> 3) is a [128 x 128 B] slab, 16-byte chunk (c & 7) of
-                    // this row sits at chunk index (c & 7) ^ (row & 7)
-                    const uint32_t dst = prow_u32 + (c >> 3) * 16384 + ((((c & 7) ^ (row & 7))) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                                 : "memory");
+                    l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
                 }
-                l += sum;
                 fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 tc_fence_before();
                 __syncwarp();
@@ -328,25 +373,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
             const float inv = 1.f / l;
             uint16_t* orow = static_cast<uint16_t*>(p.out) + (static_cast<size_t>(b) * p.S + tok) * p.D + h * DH;
             const bool tok_ok = tok < p.S;
+            uint32_t o[C::DHP];
 #pragma unroll
-            for (int c = 0; c < C::DHP / 16; ++c) {
-                uint32_t o[16];
-                tmem_ld_32x16(o_addr + c * 16, o);
-                tmem_ld_wait();
-                if (c == C::DHP / 16 - 1) {  // last read of O: hand the accumulator back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&o_empty[qb]);
-                }
-                uint32_t w[8];
+            for (int c = 0; c < C::DHP / 16; ++c) tmem_ld_32x16(o_addr + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&o[c * 16]));
+            tmem_ld_wait();
+            tc_fence_before();  // O is in registers: hand the accumulator back to the MMA warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_empty[qb]);
+            if (tok_ok) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float x0 = __uint_as_float(o[2 * i]) * inv, x1 = __uint_as_float(o[2 * i + 1]) * inv;
-                    w[i] = f16 ? pack_f16x2(x0, x1) : pack_bf16x2(x0, x1);
-                }
-                if (tok_ok) {
-                    if (c * 16 < DH) *reinterpret_cast<uint4*>(orow + c * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                    if (c * 16 + 8 < DH) *reinterpret_cast<uint4*>(orow + c * 16 + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                for (int c = 0; c < C::DHP / 8; ++c) {
+                    if (c * 8 < DH) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float x0 = __uint_as_float(o[c * 8 + 2 * i]) * inv, x1 = __uint_as_float(o[c * 8 + 2 * i + 1]) * inv;
+                            w[i] = f16 ? pack_f16x2(x0, x1) : pack_bf16x2(x0, x1);
+                        }
+                        *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
                 }
             }
         }
@@ -442,6 +487,10 @@ int launch_tc(const void* qkv, bool f16, int batch, int tokens, int heads, void*
     p.num_items = batch * heads * p.nqp;
     p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
     p.f16 = f16 ? 1 : 0;
+    {
+        const char* e = getenv("VLMFW_ATTN_DBG");
+        p.dbg = e ? atoi(e) : 0;
+    }
     const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
     kern<<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(mp.main, mp.tail, p);
     VLMFW_LAUNCH_CHECK();
