@@ -179,7 +179,13 @@ int vlmfw_probe_bn_running_update(float* running_mean, float* running_var, const
  * VLMFW_EPI_BIAS_RESID_F32 writes fp32 acc + bias + resid.
  * Row mapping of the output: out_row = (m / grp) * grp_out + (m % grp) + grp_off  (grp <= 0: out_row = m).
  * resid row = m % resid_mod (resid_mod <= 0: m). K, lda, ldw multiples of 8; N, ldo multiples of 8.
- * block_n: N tile of the kernel (128 / 192 / 256), 0 = choose the one that wastes the fewest MMA columns. */
+ * block_n: N tile of the kernel (128 / 192 / 256), 0 = choose the one that wastes the fewest MMA columns; OR-ed with
+ * VLMFW_GEMM_FORCE_1CTA / VLMFW_GEMM_FORCE_2CTA to pin the single-CTA (128-row tiles) or CTA-pair (tcgen05
+ * cta_group::2, 256-row tiles) form of the kernel — by default pairs are used whenever M > 128. */
+#define VLMFW_GEMM_FORCE_1CTA 0x1000
+#define VLMFW_GEMM_FORCE_2CTA 0x2000
+/* test hook: use the transpose-and-store epilogue (normally only taken for grp / resid_mod) instead of the TMA one */
+#define VLMFW_GEMM_FORCE_GENERIC_EPI 0x4000
 int vlmfw_gemm_tn(const void* a, int32_t lda, const void* w, int32_t ldw, int32_t dtype, int32_t m, int32_t n,
                   int32_t k, const float* bias, int32_t epi, int32_t act, void* out, int32_t ldo, const float* resid,
                   int32_t ldr, int32_t resid_mod, int32_t grp, int32_t grp_out, int32_t grp_off, int32_t block_n,

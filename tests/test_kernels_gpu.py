@@ -30,13 +30,18 @@ GEMM_SHAPES = [(256, 256, 128), (128, 128, 64), (384, 1152, 1152), (1000, 3456, 
                (520, 1152, 4304), (777, 1152, 592), (64, 144, 144), (130, 432, 144), (40, 176, 384)]
 
 
+# kernel forms: single CTA (128-row tiles) and CTA pair (tcgen05 cta_group::2, 256-row tiles); include/vlmfw_b200.h
+FORMS = {"auto": 0, "1cta": 0x1000, "2cta": 0x2000, "1cta-generic-epi": 0x5000, "2cta-generic-epi": 0x6000}
+
+
 @pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
 @pytest.mark.parametrize("block_n", [0, 128, 192, 256])
-def test_gemm_bias_bf16(cuda_device, m, n, k, block_n):
+@pytest.mark.parametrize("form", list(FORMS))
+def test_gemm_bias_bf16(cuda_device, m, n, k, block_n, form):
     a = _rand((m, k), 1).to(torch.bfloat16)
     w = _rand((n, k), 2, 1 / math.sqrt(k)).to(torch.bfloat16)
     bias = _rand((n,), 3, 0.5)
-    out = ops.gemm_tn(a, w, bias, block_n=block_n)
+    out = ops.gemm_tn(a, w, bias, block_n=block_n | FORMS[form])
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t() + bias
     # fp32 accumulate of exact bf16 products; only the final bf16 rounding (rel 2^-8) differs
@@ -46,41 +51,64 @@ def test_gemm_bias_bf16(cuda_device, m, n, k, block_n):
 
 
 @pytest.mark.parametrize("act", [specs.ACT_GELU_TANH, specs.ACT_QUICK_GELU, specs.ACT_GELU_ERF])
-def test_gemm_activation(cuda_device, act):
+@pytest.mark.parametrize("form", ["1cta", "2cta"])
+def test_gemm_activation(cuda_device, act, form):
     m, n, k = 300, 4304, 1152
     a = _rand((m, k), 4).to(torch.bfloat16)
     w = _rand((n, k), 5, 2 / math.sqrt(k)).to(torch.bfloat16)
     bias = _rand((n,), 6, 0.5)
-    out = ops.gemm_tn(a, w, bias, act=act)
+    out = ops.gemm_tn(a, w, bias, act=act, block_n=FORMS[form])
     ref = _act_ref(a.float() @ w.float().t() + bias, act)
     torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
 
 
-@pytest.mark.parametrize("m,n,k", [(384, 1152, 1152), (777, 1152, 4304), (130, 144, 304), (64, 1408, 6144)])
-def test_gemm_residual_f32_inplace(cuda_device, m, n, k):
+@pytest.mark.parametrize("m,n,k", [(384, 1152, 1152), (777, 1152, 4304), (130, 144, 304), (64, 1408, 6144),
+                                   (40000, 1152, 1152)])
+@pytest.mark.parametrize("form", ["1cta", "2cta", "1cta-generic-epi", "2cta-generic-epi"])
+def test_gemm_residual_f32_inplace(cuda_device, m, n, k, form):
     a = _rand((m, k), 7).to(torch.bfloat16)
     w = _rand((n, k), 8, 1 / math.sqrt(k)).to(torch.bfloat16)
     bias = _rand((n,), 9, 0.5)
     h = _rand((m, n), 10)
     ref = a.float() @ w.float().t() + bias + h
-    out = ops.gemm_tn(a, w, bias, resid=h, out=h)  # in place, as the tower does for the residual stream
+    out = ops.gemm_tn(a, w, bias, resid=h, out=h, block_n=FORMS[form])  # in place, as the tower does for the residual stream
     assert out.data_ptr() == h.data_ptr()
     # fp32 end to end: only accumulation-order error
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-4)
 
 
-def test_gemm_patch_embed_row_remap(cuda_device):
+@pytest.mark.parametrize("form", ["1cta", "2cta"])
+def test_gemm_patch_embed_row_remap(cuda_device, form):
     # rows of image b land at b*S + 1 + p (class-token slot left free), residual = pos[p] broadcast over images
     b, p, s, n, k = 3, 25, 26, 128, 592
     a = _rand((b * p, k), 11).to(torch.bfloat16)
     w = _rand((n, k), 12, 1 / math.sqrt(k)).to(torch.bfloat16)
     pos = _rand((p, n), 13)
     out = torch.full((b * s, n), -7.0, device="cuda")
-    ops.gemm_tn(a, w, None, resid=pos, resid_mod=p, out=out, grp=p, grp_out=s, grp_off=1)
+    ops.gemm_tn(a, w, None, resid=pos, resid_mod=p, out=out, grp=p, grp_out=s, grp_off=1, block_n=FORMS[form])
     ref = (a.float() @ w.float().t()).view(b, p, n) + pos
     got = out.view(b, s, n)
     torch.testing.assert_close(got[:, 1:], ref, rtol=1e-4, atol=2e-4)
     assert (got[:, 0] == -7.0).all()
+
+
+@pytest.mark.parametrize("form", ["1cta", "2cta"])
+def test_gemm_residual_f32_out_of_place(cuda_device, form):
+    # resid and out are different buffers with different leading dimensions (two TMA maps)
+    m, n, k = 700, 432, 304
+    a = _rand((m, k), 14).to(torch.float16)
+    w = _rand((n, k), 15, 1 / math.sqrt(k)).to(torch.float16)
+    bias = _rand((n,), 16, 0.5)
+    big = _rand((m, n + 16), 17)
+    resid = big[:, :n]
+    out = torch.zeros(m, n, device="cuda")
+    with torch.cuda.device(0):
+        from vlmfw_b200 import _lib
+        _lib.check(_lib.load().vlmfw_gemm_tn(a.data_ptr(), k, w.data_ptr(), k, _lib.DT_F16, m, n, k, bias.data_ptr(),
+                                            ops.EPI_BIAS_RESID_F32, 0, out.data_ptr(), n, resid.data_ptr(), n + 16, 0,
+                                            0, 0, 0, FORMS[form], torch.cuda.current_stream().cuda_stream))
+    ref = a.float() @ w.float().t() + bias + resid
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-4)
 
 
 def test_gemm_rejects_bad_arguments(cuda_device):

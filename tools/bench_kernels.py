@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--m", type=int, default=65536)
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--only", default="")
+    ap.add_argument("--no-cublas", action="store_true")
     args = ap.parse_args()
     m = args.m
     dev = "cuda"
@@ -57,7 +58,7 @@ def main():
         med, best = timeit(fn)
         wt = w.t()
         cb_out = torch.empty(m, n, dtype=DT, device=dev)
-        cmed, cbest = timeit(lambda: torch.matmul(a, wt, out=cb_out))
+        cmed, cbest = (float("nan"), float("nan")) if args.no_cublas else timeit(lambda: torch.matmul(a, wt, out=cb_out))
         rows.append({"kernel": name, "m": m, "n": n, "k": k, "epi": kind, "ms": round(med, 4), "tflops": round(flops / med / 1e9, 1),
                      "best_tflops": round(flops / best / 1e9, 1), "cublas_ms": round(cmed, 4),
                      "cublas_tflops": round(flops / cmed / 1e9, 1)})

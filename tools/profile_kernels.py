@@ -35,5 +35,7 @@ for it in range(2):
     mid = ops.gemm_tn(xn, w1, b1, act=spec.act)
     ops.gemm_tn(mid, w2, b2, resid=h, out=h)
     pooled = ops.pool(h.view(B, spec.tokens, D), specs.POOL_LN_MEAN, gamma, beta, 1e-6)
+    if os.environ.get("VLMFW_PROFILE_CUBLAS") == "1":  # the library GEMM on the fc1 shape, for a side-by-side ncu read
+        torch.matmul(xn, w1.t())
     torch.cuda.synchronize()
 print("ok", float(pooled.float().abs().mean()))

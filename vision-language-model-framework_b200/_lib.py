@@ -11,7 +11,8 @@ import subprocess
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvlmfw_b200.so")
+# VLMFW_B200_LIB: kernel-tuning experiments load an alternative build of the same sources (tools/ only)
+LIB_PATH = os.environ.get("VLMFW_B200_LIB") or os.path.join(_HERE, "libvlmfw_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 OK, E_INVALID, E_NODEVICE, E_CUDA, E_STATE, E_NOTFOUND = 0, -1, -2, -3, -4, -5

@@ -11,11 +11,22 @@
 // Structure (one persistent CTA per SM, 320 threads, warp-specialised):
 //   warp 0      : TMA producer   — 128B-swizzled [128 x 64] A tiles and [BN x 64] W tiles into a STAGES-deep ring
 //   warp 1      : MMA issuer     — one lane issues tcgen05.mma 128 x BN x 16, commits free ring slots / signal epilogue
-//   warps 2..9  : epilogue       — tcgen05.ld 32x32 fp32 chunks, transpose through swizzled smem, fused bias /
-//                                  activation / residual, fully coalesced global stores
+//   warps 2..9  : epilogue       — one thread = one output row (= one TMEM lane): tcgen05.ld a 32-column chunk, fused
+//                                  bias / activation / residual in registers, the chunk goes out through a swizzled
+//                                  smem box and a TMA store; the fp32 residual chunk comes IN through a 3-deep ring
+//                                  of TMA loads issued two chunks ahead. No global address arithmetic, no bounds
+//                                  predicates (TMA clips ragged M / N) and no accumulator transpose.
+//                                  (GEN = true keeps the older transpose-and-store epilogue for the row-remapped /
+//                                  broadcast-residual case the patch embedding needs.)
 // TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// CG = 2 runs the same roles on a CTA PAIR (cluster of two CTAs on one TPC, tcgen05 cta_group::2): the pair owns a
+// 256 x BN tile, each CTA stages its own 128 rows of A and HALF of the W tile (BN/2 rows), the leader CTA's MMA lane
+// issues 256 x BN x 16 instructions that read both halves, and each CTA's epilogue drains its own 128 TMEM lanes.
+// Per SM that halves the W bytes moved L2 -> smem and smem -> tensor core, which is what bounds the single-CTA form.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -31,17 +42,35 @@ constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
-constexpr int STAGING_PER_WARP = 32 * 128;  // 32 rows x 32 fp32
+constexpr int STAGING_PER_WARP = 32 * 128;  // generic epilogue: 32 rows x 32 fp32
+#ifndef VLMFW_RES_NBUF
+#define VLMFW_RES_NBUF 2
+#endif
+#ifndef VLMFW_RES_COLS
+#define VLMFW_RES_COLS 32
+#endif
+constexpr int RES_NBUF = VLMFW_RES_NBUF;  // residual epilogue: ring of [32 rows x RES_COLS fp32] TMA boxes per warp
+constexpr int RES_COLS = VLMFW_RES_COLS;  // 32 (128B-swizzled boxes) or 16 (64B-swizzled)
+static_assert(RES_COLS == 16 || RES_COLS == 32, "residual box is 16 or 32 fp32 columns wide");
+constexpr int SMEM_LIMIT = 232448;          // 227 KB opt-in maximum per CTA
 
-template <int BN>
+template <int BN, int CG, int EPI, bool GEN>
 struct Cfg {
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_ROWS = BN / CG;  // W rows staged by one CTA
+    static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 128) ? 6 : 4;
+    // per-warp epilogue staging: generic 4 KB transpose buffer; 16-bit TMA-store path 2 x [32 x 64 B] boxes;
+    // residual path RES_NBUF x [32 x RES_COLS fp32] boxes
+    static constexpr int STG_PER_WARP =
+        GEN ? STAGING_PER_WARP : (EPI == VLMFW_EPI_BIAS_RESID_F32 ? RES_NBUF * 32 * RES_COLS * 4 : 2 * 2048);
+    static constexpr int STAGING_BYTES = EPI_WARPS * STG_PER_WARP;
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int RING_MAX = (SMEM_LIMIT - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = RING_MAX > 6 ? 6 : RING_MAX;
+    static_assert(STAGES >= 2, "operand ring needs at least two stages");
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STAGING_PER_WARP + BAR_BYTES + 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
 };
 
 struct KParams {
@@ -55,16 +84,22 @@ struct KParams {
     int ldr;
     int resid_mod;
     int grp, grp_out, grp_off;
+    int dbg;  // VLMFW_GEMM_DBG bit mask (bottleneck experiments only): 1 no TMA after the ring is primed, 2 no epilogue
+              // global traffic, 4 no MMA issue
 };
 
 template <int ACT>
 __device__ __forceinline__ float activation(float x) {
     if constexpr (ACT == VLMFW_ACT_GELU_TANH) {
-        // 0.5 x (1 + tanh(u)) == x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3)   (activations.py gelu_pytorch_tanh)
-        float u = 1.5957691216057308f * (x + 0.044715f * x * x * x);
-        return __fdividef(x, 1.0f + __expf(-u));
+        // 0.5 x (1 + tanh(u)) == x * sigmoid(2u) = x / (1 + 2^(-2u log2 e)), u = sqrt(2/pi) (x + 0.044715 x^3)
+        // (activations.py gelu_pytorch_tanh); the constants are folded so the exponent costs FMUL + FFMA + FMUL
+        constexpr float B = -1.5957691216057308f * 1.4426950408889634f;  // -2 sqrt(2/pi) log2(e)
+        constexpr float A = B * 0.044715f;
+        const float e = ex2_approx(x * fmaf(x * x, A, B));
+        return __fdividef(x, 1.0f + e);
     } else if constexpr (ACT == VLMFW_ACT_QUICK_GELU) {
-        return __fdividef(x, 1.0f + __expf(-1.702f * x));  // x * sigmoid(1.702 x)  (activations.py QuickGELU)
+        // x * sigmoid(1.702 x)  (activations.py QuickGELU)
+        return __fdividef(x, 1.0f + ex2_approx(x * (-1.702f * 1.4426950408889634f)));
     } else if constexpr (ACT == VLMFW_ACT_GELU_ERF) {
         return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
     } else {
@@ -72,25 +107,32 @@ __device__ __forceinline__ float activation(float x) {
     }
 }
 
-template <int BN, int EPI, int ACT>
+template <int BN, int EPI, int ACT, int CG, bool GEN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const KParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CG, EPI, GEN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_WARPS * STAGING_PER_WARP);
+    uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;  // 1024-byte aligned: every stage is a multiple of 1 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C::STAGING_BYTES);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + C::STAGES;
     uint64_t* tmem_full = bars + 2 * C::STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_bar = tmem_empty + 2;  // [EPI_WARPS][RES_NBUF], residual epilogue only
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS * RES_NBUF);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int m_tiles = (p.m + BM - 1) / BM;
+    // a "worker" is one CTA (CG = 1) or one CTA pair (CG = 2); it owns TILE_M x BN output tiles
+    constexpr int TILE_M = BM * CG;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const int worker = static_cast<int>(blockIdx.x) / CG;
+    const int num_workers = static_cast<int>(gridDim.x) / CG;
+    const int m_tiles = (p.m + TILE_M - 1) / TILE_M;
     const int n_tiles = (p.n + BN - 1) / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = (p.k + BK - 1) / BK;
@@ -104,16 +146,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], EPI_WARPS);
+            mbar_init(&tmem_empty[s], EPI_WARPS * CG);  // pair: the leader's barrier collects both CTAs' epilogue warps
+        }
+        for (int s = 0; s < EPI_WARPS * RES_NBUF; ++s) mbar_init(&res_bar[s], 1);
+        if constexpr (!GEN) {
+            tma_prefetch_desc(&tmap_out);
+            if constexpr (EPI == VLMFW_EPI_BIAS_RESID_F32) tma_prefetch_desc(&tmap_res);
         }
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, C::TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (CG == 2) {
+            tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_slot, C::TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must exist before anything is signalled on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -122,16 +175,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * BM;
-                const int n0 = (tile % n_tiles) * BN;
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const int m0 = (tile / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM;
+                const int n0 = (tile % n_tiles) * BN + static_cast<int>(cta_rank) * C::B_ROWS;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
                     uint8_t* sb = sa + C::A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
-                    tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * BK, n0);
+                    if ((p.dbg & 1) && (tile != worker || kb >= C::STAGES)) {
+                        if (cta_rank == 0) mbar_arrive(&full_bar[stage]);
+                    } else if constexpr (CG == 2) {
+                        // both CTAs load into their own smem; all bytes are counted on the LEADER's full barrier
+                        const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                        tma_load_2d_pair(sa, &tmap_a, lead_bar, kb * BK, m0);
+                        tma_load_2d_pair(sb, &tmap_w, lead_bar, kb * BK, n0);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+                        tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * BK, n0);
+                    }
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -141,13 +204,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (lane == 0 && cta_rank == 0) {
             const uint32_t idesc = p.idesc;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -159,12 +222,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint64_t bdesc = umma_desc_sw128(sa + C::A_BYTES);
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                        if (p.dbg & 4) break;
                         // advancing K inside the 128B swizzle row: +32 bytes -> +2 in the (addr >> 4) field
-                        umma_bf16_ss(d_tmem, adesc + static_cast<uint64_t>(ks * 2), bdesc + static_cast<uint64_t>(ks * 2),
-                                     idesc, (kb | ks) != 0 ? 1u : 0u);
+                        if constexpr (CG == 2)
+                            umma_bf16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(ks * 2),
+                                              bdesc + static_cast<uint64_t>(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
+                        else
+                            umma_bf16_ss(d_tmem, adesc + static_cast<uint64_t>(ks * 2),
+                                         bdesc + static_cast<uint64_t>(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);  // ring slot reusable once these MMAs have read it
-                    if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                    // ring slot reusable (in both CTAs of a pair) once these MMAs have read it
+                    if constexpr (CG == 2) {
+                        umma_commit_pair(&empty_bar[stage], 3);
+                        if (kb == num_kb - 1) umma_commit_pair(&tmem_full[acc], 3);
+                    } else {
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                    }
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -183,12 +257,164 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int half = ew >> 2;            // which half of the BN columns
         constexpr int COLS_PER_WARP = BN / 2;
         constexpr int CHUNKS = COLS_PER_WARP / 32;
-        uint8_t* stg = staging + ew * STAGING_PER_WARP;
+        uint8_t* stg = staging + ew * C::STG_PER_WARP;
         const uint32_t stg_u32 = smem_u32(stg);
-        const int rsub = lane >> 3;  // read-back: 4 rows per pass
-        const int cj = lane & 7;     // read-back: 16-byte column group (4 fp32)
         int acc = 0;
         uint32_t acc_phase = 0;
+        const uint32_t lead_tmem_empty = (CG == 2) ? mapa_shared(smem_u32(tmem_empty), 0) : 0u;
+        auto release_acc = [&]() {
+            // accumulator drained -> hand the TMEM buffer back to the (leader's) MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(lead_tmem_empty + static_cast<uint32_t>(acc) * 8u);
+                else mbar_arrive(&tmem_empty[acc]);
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        };
+        const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                    static_cast<uint32_t>(half * COLS_PER_WARP);
+
+        if constexpr (!GEN && EPI == VLMFW_EPI_BIAS_BF16) {
+            // ---- 16-bit output: act(acc + bias) -> fp16/bf16 -> [32 rows x 32 cols] 64B-swizzled box -> TMA store.
+            // Two boxes per warp alternate, so a store may still be reading one while the next chunk is written.
+            const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;  // SWIZZLE_64B: 16B chunk ^= (row / 2) % 4
+            const uint32_t row_u32 = stg_u32 + static_cast<uint32_t>(lane) * 64u;
+            uint32_t q = 0;
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const int m0 = (tile / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
+                const int n0 = (tile % n_tiles) * BN + half * COLS_PER_WARP;
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld_32x32(lane_taddr + static_cast<uint32_t>(acc * BN), v);
+#pragma unroll 1
+                for (int c = 0; c < CHUNKS; ++c, ++q) {
+                    const int nc = n0 + c * 32;
+                    tmem_ld_wait();
+                    float y[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias != nullptr && nc + 4 * j < p.n) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 4 * j));
+                        y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bv.x;
+                        y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv.y;
+                        y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv.z;
+                        y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv.w;
+                    }
+                    // the next chunk's TMEM read flies while this one is activated, packed and stored
+                    if (c + 1 < CHUNKS) tmem_ld_32x32(lane_taddr + static_cast<uint32_t>(acc * BN + (c + 1) * 32), v);
+                    uint32_t o[16];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) y[j] = activation<ACT>(y[j]);
+                    if (p.out_f16) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = pack_f16x2(y[2 * j], y[2 * j + 1]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(y[2 * j], y[2 * j + 1]);
+                    }
+                    if (p.dbg & 2) continue;
+                    const uint32_t box = row_u32 + (q & 1u) * 2048u;
+                    if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago has left this box
+                    __syncwarp();
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + ((j ^ sw) << 4)), "r"(o[4 * j]),
+                                     "r"(o[4 * j + 1]), "r"(o[4 * j + 2]), "r"(o[4 * j + 3])
+                                     : "memory");
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_out, stg_u32 + (q & 1u) * 2048u, nc, m0);
+                        tma_store_commit();
+                    }
+                }
+                release_acc();
+            }
+            if (lane == 0) tma_store_wait_all();
+        } else if constexpr (!GEN && EPI == VLMFW_EPI_BIAS_RESID_F32) {
+            // ---- fp32 residual: out = acc + bias + resid, usually in place on the residual stream. The residual chunk
+            // [32 rows x RES_COLS fp32] arrives by TMA in a swizzled box (ring of RES_NBUF per warp, loads issued
+            // RES_NBUF - 1 chunks ahead, across tile boundaries), every thread updates its own row in place, and the
+            // same box is TMA-stored. Narrow boxes buy ring depth (HBM latency) without taking smem from the operand
+            // ring, which needs its stages more (measured: 5 stages beat 4 by 3-7 % on every residual GEMM).
+            constexpr int RCHUNKS = COLS_PER_WARP / RES_COLS;
+            constexpr uint32_t ROW_BYTES = RES_COLS * 4;
+            constexpr uint32_t BOX_BYTES = 32 * ROW_BYTES;
+            const uint32_t sw = (RES_COLS == 32) ? (static_cast<uint32_t>(lane) & 7u) : ((static_cast<uint32_t>(lane) >> 1) & 3u);
+            uint64_t* my_bar = res_bar + ew * RES_NBUF;
+            const int my_tiles = worker < num_tiles ? (num_tiles - worker + num_workers - 1) / num_workers : 0;
+            const uint32_t total_q = static_cast<uint32_t>(my_tiles) * RCHUNKS;
+            auto issue_load = [&](uint32_t qq) {  // lane 0 only
+                const int t = worker + static_cast<int>(qq / RCHUNKS) * num_workers;
+                const int c = static_cast<int>(qq % RCHUNKS);
+                const int cx = (t % n_tiles) * BN + half * COLS_PER_WARP + c * RES_COLS;
+                const int cy = (t / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
+                const uint32_t b = qq % RES_NBUF;
+                mbar_arrive_expect_tx(&my_bar[b], BOX_BYTES);
+                tma_load_2d(stg + b * BOX_BYTES, &tmap_res, &my_bar[b], cx, cy);
+            };
+            if (lane == 0 && !(p.dbg & 2)) {
+                for (uint32_t qq = 0; qq < RES_NBUF - 1 && qq < total_q; ++qq) issue_load(qq);
+            }
+            uint32_t q = 0;
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const int m0 = (tile / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
+                const int n0 = (tile % n_tiles) * BN + half * COLS_PER_WARP;
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < RCHUNKS; ++c, ++q) {
+                    if (p.dbg & 2) continue;
+                    const int nc = n0 + c * RES_COLS;
+                    uint32_t v[RES_COLS];
+                    const uint32_t taddr = lane_taddr + static_cast<uint32_t>(acc * BN + c * RES_COLS);
+                    tmem_ld_row(taddr, v);
+                    const uint32_t b = q % RES_NBUF;
+                    const uint32_t box = stg_u32 + b * BOX_BYTES + static_cast<uint32_t>(lane) * ROW_BYTES;
+                    mbar_wait(&my_bar[b], (q / RES_NBUF) & 1u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (uint32_t j = 0; j < RES_COLS / 4; ++j) {
+                        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias != nullptr && nc + 4 * static_cast<int>(j) < p.n)
+                            bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 4 * j));
+                        const uint32_t a = box + ((j ^ sw) << 4);
+                        float4 r;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                                     : "r"(a));
+                        r.x += __uint_as_float(v[4 * j + 0]) + bv.x;
+                        r.y += __uint_as_float(v[4 * j + 1]) + bv.y;
+                        r.z += __uint_as_float(v[4 * j + 2]) + bv.z;
+                        r.w += __uint_as_float(v[4 * j + 3]) + bv.w;
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r.x), "f"(r.y), "f"(r.z),
+                                     "f"(r.w)
+                                     : "memory");
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_out, stg_u32 + b * BOX_BYTES, nc, m0);
+                        tma_store_commit();
+                        // the box of chunk q + NBUF - 1 is the one chunk q - 1 was stored from: that store (every bulk
+                        // group but the newest, or the newest too when the ring has two boxes) must have read it
+                        tma_store_wait_read<(RES_NBUF > 2) ? 1 : 0>();
+                        if (q + RES_NBUF - 1 < total_q) issue_load(q + RES_NBUF - 1);
+                    }
+                    __syncwarp();
+                }
+                release_acc();
+            }
+            if (lane == 0) tma_store_wait_all();
+        } else {
+        const int rsub = lane >> 3;  // read-back: 4 rows per pass
+        const int cj = lane & 7;     // read-back: 16-byte column group (4 fp32)
 
         // Residual epilogue: the fp32 residual tile is the only global READ of the epilogue and it does not depend on
         // the accumulator, so it is software-pipelined one 32-column chunk ahead (across tile boundaries too): the
@@ -196,7 +422,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         float4 rnext[8];
         auto resid_issue = [&](int tile, int c, float4 (&r)[8]) {
             if constexpr (EPI == VLMFW_EPI_BIAS_RESID_F32) {
-                const int m0 = (tile / n_tiles) * BM + quarter * 32;
+                if (p.dbg & 2) return;
+                const int m0 = (tile / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
                 const int col = (tile % n_tiles) * BN + half * COLS_PER_WARP + c * 32 + cj * 4;
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
@@ -209,10 +436,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
         };
-        if (blockIdx.x < num_tiles) resid_issue(blockIdx.x, 0, rnext);
+        if (worker < num_tiles) resid_issue(worker, 0, rnext);
 
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles) * BM + quarter * 32;
+        for (int tile = worker; tile < num_tiles; tile += num_workers) {
+            const int m0 = (tile / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
             const int n0 = (tile % n_tiles) * BN + half * COLS_PER_WARP;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -225,9 +452,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int it = 0; it < 8; ++it) rcur[it] = rnext[it];
                     // next chunk of this tile, or chunk 0 of this CTA's next tile
                     if (c + 1 < CHUNKS) resid_issue(tile, c + 1, rnext);
-                    else if (tile + static_cast<int>(gridDim.x) < num_tiles) resid_issue(tile + gridDim.x, 0, rnext);
+                    else if (tile + num_workers < num_tiles) resid_issue(tile + num_workers, 0, rnext);
                 }
-                if (nc >= p.n) continue;  // warp-uniform: whole chunk is past the N edge (prefetch above still ran)
+                if (nc >= p.n || (p.dbg & 2)) continue;  // warp-uniform: whole chunk is past the N edge (prefetch above still ran)
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                        static_cast<uint32_t>(acc * BN + half * COLS_PER_WARP + c * 32);
@@ -282,22 +509,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 __syncwarp();
             }
-            // accumulator drained -> hand the TMEM buffer back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            if (++acc == 2) {
-                acc = 0;
-                acc_phase ^= 1;
-            }
+            release_acc();
         }
+        }  // generic epilogue
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its smem
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, C::TMEM_COLS);
+        if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+        else tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -319,9 +542,10 @@ EncodeTiledFn encode_fn() {
 
 struct MapKey {
     const void* ptr;
-    int rows, cols, ld, box_rows, f16;
+    int rows, cols, ld, box_rows, box_cols, dt, swz;
     bool operator==(const MapKey& o) const {
-        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && f16 == o.f16;
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+               box_cols == o.box_cols && dt == o.dt && swz == o.swz;
     }
 };
 struct MapKeyHash {
@@ -330,17 +554,20 @@ struct MapKeyHash {
         h ^= (static_cast<size_t>(k.rows) * 0x9E3779B97F4A7C15ull) + (h << 6) + (h >> 2);
         h ^= (static_cast<size_t>(k.cols) * 0xC2B2AE3D27D4EB4Full) + (h << 6) + (h >> 2);
         h ^= (static_cast<size_t>(k.ld) * 0x165667B19E3779F9ull) + (h << 6) + (h >> 2);
-        h ^= static_cast<size_t>(k.box_rows * 2 + k.f16) + (h << 6) + (h >> 2);
+        h ^= static_cast<size_t>(((k.box_rows * 512 + k.box_cols) * 4 + k.dt) * 256 + k.swz) + (h << 6) + (h >> 2);
         return h;
     }
 };
 
-// [rows, cols] bf16 row-major (row stride ld elements) -> tiled map with box {64 cols, box_rows}, 128B swizzle,
-// out-of-bounds elements read as zero (this is what makes ragged M / N / K edges free).
-int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, bool f16, CUtensorMap* out) {
+enum MapDt { MAP_BF16 = 0, MAP_F16 = 1, MAP_F32 = 2 };
+
+// [rows, cols] row-major matrix (row stride ld elements) -> tiled map with box {box_cols, box_rows} and the given
+// swizzle; out-of-bounds elements read as zero and are not written (this is what makes ragged M / N / K edges free).
+int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols, MapDt dt, int swizzle_bytes,
+                   CUtensorMap* out) {
     static std::mutex mu;
     static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    MapKey key{ptr, rows, cols, ld, box_rows, f16 ? 1 : 0};
+    MapKey key{ptr, rows, cols, ld, box_rows, box_cols, static_cast<int>(dt), swizzle_bytes};
     {
         std::lock_guard<std::mutex> lk(mu);
         auto it = cache.find(key);
@@ -354,17 +581,21 @@ int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, bo
         set_error("cuTensorMapEncodeTiled entry point unavailable");
         return VLMFW_E_CUDA;
     }
+    const int esize = dt == MAP_F32 ? 4 : 2;
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * esize};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estride[2] = {1, 1};
+    const CUtensorMapDataType cdt = dt == MAP_F32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                    : dt == MAP_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                    : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap tm;
-    CUresult r = fn(&tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estride,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(&tm, cdt, 2, const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (CUresult %d) ptr=%p rows=%d cols=%d ld=%d box_rows=%d",
-                  static_cast<int>(r), ptr, rows, cols, ld, box_rows);
+        set_error("cuTensorMapEncodeTiled failed (CUresult %d) ptr=%p rows=%d cols=%d ld=%d box=%dx%d dt=%d",
+                  static_cast<int>(r), ptr, rows, cols, ld, box_rows, box_cols, static_cast<int>(dt));
         return VLMFW_E_CUDA;
     }
     {
@@ -376,15 +607,29 @@ int get_tensor_map(const void* ptr, int rows, int cols, int ld, int box_rows, bo
     return VLMFW_OK;
 }
 
-template <int BN, int EPI, int ACT>
+template <int BN, int EPI, int ACT, int CG, bool GEN>
 int launch_one(const GemmArgs& g, cudaStream_t stream) {
-    using C = Cfg<BN>;
-    CUtensorMap ta, tw;
-    int rc = get_tensor_map(g.a, g.m, g.k, g.lda, BM, g.f16, &ta);
+    using C = Cfg<BN, CG, EPI, GEN>;
+    const MapDt dt16 = g.f16 ? MAP_F16 : MAP_BF16;
+    CUtensorMap ta, tw, tout, tres;
+    int rc = get_tensor_map(g.a, g.m, g.k, g.lda, BM, BK, dt16, 128, &ta);
     if (rc != VLMFW_OK) return rc;
-    rc = get_tensor_map(g.w, g.n, g.k, g.ldw, BN, g.f16, &tw);
+    rc = get_tensor_map(g.w, g.n, g.k, g.ldw, C::B_ROWS, BK, dt16, 128, &tw);
     if (rc != VLMFW_OK) return rc;
-    auto kern = gemm_bf16_tn_kernel<BN, EPI, ACT>;
+    tout = ta;  // unused by the generic epilogue, but a kernel parameter must be a valid object
+    tres = ta;
+    if constexpr (!GEN) {
+        if constexpr (EPI == VLMFW_EPI_BIAS_RESID_F32) {
+            rc = get_tensor_map(g.out, g.m, g.n, g.ldo, 32, RES_COLS, MAP_F32, RES_COLS * 4, &tout);
+            if (rc != VLMFW_OK) return rc;
+            rc = get_tensor_map(g.resid, g.m, g.n, g.ldr, 32, RES_COLS, MAP_F32, RES_COLS * 4, &tres);
+            if (rc != VLMFW_OK) return rc;
+        } else {
+            rc = get_tensor_map(g.out, g.m, g.n, g.ldo, 32, 32, dt16, 64, &tout);
+            if (rc != VLMFW_OK) return rc;
+        }
+    }
+    auto kern = gemm_bf16_tn_kernel<BN, EPI, ACT, CG, GEN>;
     static bool attr_set = false;
     if (!attr_set) {
         VLMFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -394,7 +639,7 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
     p.m = g.m;
     p.n = g.n;
     p.k = g.k;
-    p.idesc = umma_idesc_16(BM, BN, g.f16, g.f16);
+    p.idesc = umma_idesc_16(BM * CG, BN, g.f16, g.f16);
     p.out_f16 = g.f16 ? 1 : 0;
     p.bias = g.bias;
     p.out = g.out;
@@ -405,41 +650,91 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
     p.grp = g.grp;
     p.grp_out = g.grp_out;
     p.grp_off = g.grp_off;
-    const int m_tiles = (g.m + BM - 1) / BM;
+    static const int dbg = []() {
+        const char* e = getenv("VLMFW_GEMM_DBG");
+        return e ? atoi(e) : 0;
+    }();
+    p.dbg = dbg;
+    constexpr int TILE_M = BM * CG;
+    const int m_tiles = (g.m + TILE_M - 1) / TILE_M;
     const int n_tiles = (g.n + BN - 1) / BN;
     const int tiles = m_tiles * n_tiles;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tw, p);
+    const int workers = num_sms() / CG;
+    const int grid = (tiles < workers ? tiles : workers) * CG;
+    if constexpr (CG == 2) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        VLMFW_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tw, tout, tres, p));
+    } else {
+        kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tw, tout, tres, p);
+    }
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 int dispatch_epi(const GemmArgs& g, cudaStream_t stream) {
-    if (g.epi == VLMFW_EPI_BIAS_RESID_F32) return launch_one<BN, VLMFW_EPI_BIAS_RESID_F32, VLMFW_ACT_NONE>(g, stream);
+    // row remap (patch embedding around the class-token slot) and a broadcast residual (position embedding) go through
+    // the generic epilogue; everything else moves its output (and residual) with TMA
+    const bool generic = g.grp > 0 || g.resid_mod > 0 || (g.block_n & VLMFW_GEMM_FORCE_GENERIC_EPI);
+    if (g.epi == VLMFW_EPI_BIAS_RESID_F32) {
+        if (generic) return launch_one<BN, VLMFW_EPI_BIAS_RESID_F32, VLMFW_ACT_NONE, CG, true>(g, stream);
+        return launch_one<BN, VLMFW_EPI_BIAS_RESID_F32, VLMFW_ACT_NONE, CG, false>(g, stream);
+    }
+    if (generic) {
+        VLMFW_REQUIRE(g.act == VLMFW_ACT_NONE, "gemm: the row-remapped 16-bit epilogue has no fused activation");
+        return launch_one<BN, VLMFW_EPI_BIAS_BF16, VLMFW_ACT_NONE, CG, true>(g, stream);
+    }
     switch (g.act) {
         case VLMFW_ACT_GELU_TANH:
-            return launch_one<BN, VLMFW_EPI_BIAS_BF16, VLMFW_ACT_GELU_TANH>(g, stream);
+            return launch_one<BN, VLMFW_EPI_BIAS_BF16, VLMFW_ACT_GELU_TANH, CG, false>(g, stream);
         case VLMFW_ACT_QUICK_GELU:
-            return launch_one<BN, VLMFW_EPI_BIAS_BF16, VLMFW_ACT_QUICK_GELU>(g, stream);
+            return launch_one<BN, VLMFW_EPI_BIAS_BF16, VLMFW_ACT_QUICK_GELU, CG, false>(g, stream);
         case VLMFW_ACT_GELU_ERF:
-            return launch_one<BN, VLMFW_EPI_BIAS_BF16, VLMFW_ACT_GELU_ERF>(g, stream);
+            return launch_one<BN, VLMFW_EPI_BIAS_BF16, VLMFW_ACT_GELU_ERF, CG, false>(g, stream);
         default:
-            return launch_one<BN, VLMFW_EPI_BIAS_BF16, VLMFW_ACT_NONE>(g, stream);
+            return launch_one<BN, VLMFW_EPI_BIAS_BF16, VLMFW_ACT_NONE, CG, false>(g, stream);
     }
 }
 
-// Pick the N tile that wastes the fewest MMA columns; ties go to the wider tile (less A re-streaming).
+template <int CG>
+int dispatch_bn(int bn, const GemmArgs& g, cudaStream_t stream) {
+    switch (bn) {
+        case 256:
+            return dispatch_epi<256, CG>(g, stream);
+        case 192:
+            return dispatch_epi<192, CG>(g, stream);
+        case 128:
+            return dispatch_epi<128, CG>(g, stream);
+        default:
+            set_error("gemm: unsupported block_n %d", bn);
+            return VLMFW_E_INVALID;
+    }
+}
+
+// Pick the N tile by a measured cost model: MMA-only throughput on B200 at M = 256 (CTA pair) is 1.00 / 0.85 / 0.59 of
+// the BN = 256 rate for BN = 256 / 192 / 128 (the A-operand read does not shrink with N), so a tile costs
+// 1.00 / 0.88 / 0.85 time units; 256 wins whenever N > 192 even with a ragged last tile (TMA zero-fills it for free).
 int pick_block_n(int n) {
     const int cands[3] = {256, 192, 128};
+    const float unit[3] = {1.00f, 0.88f, 0.85f};
     int best = 256;
-    long best_cost = -1;
-    for (int bn : cands) {
-        long tiles = (n + bn - 1) / bn;
-        long cost = tiles * bn;
-        if (best_cost < 0 || cost < best_cost) {
+    float best_cost = -1.f;
+    for (int i = 0; i < 3; ++i) {
+        const float cost = static_cast<float>((n + cands[i] - 1) / cands[i]) * unit[i];
+        if (best_cost < 0.f || cost < best_cost) {
             best_cost = cost;
-            best = bn;
+            best = cands[i];
         }
     }
     return best;
@@ -494,18 +789,13 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     if (g.bias) VLMFW_REQUIRE((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
-    const int bn = g.block_n > 0 ? g.block_n : pick_block_n(g.n);
-    switch (bn) {
-        case 256:
-            return dispatch_epi<256>(g, stream);
-        case 192:
-            return dispatch_epi<192>(g, stream);
-        case 128:
-            return dispatch_epi<128>(g, stream);
-        default:
-            set_error("gemm: unsupported block_n %d", bn);
-            return VLMFW_E_INVALID;
-    }
+    const int bn_req = g.block_n & 0xFFF;
+    const int bn = bn_req > 0 ? bn_req : pick_block_n(g.n);
+    // CTA pairs (256-row tiles) unless the caller forces a form or the problem has a single 128-row tile
+    int cg = g.m > BM ? 2 : 1;
+    if (g.block_n & VLMFW_GEMM_FORCE_1CTA) cg = 1;
+    if (g.block_n & VLMFW_GEMM_FORCE_2CTA) cg = 2;
+    return cg == 2 ? dispatch_bn<2>(bn, g, stream) : dispatch_bn<1>(bn, g, stream);
 }
 
 }  // namespace vlmfw
