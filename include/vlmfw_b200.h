@@ -190,6 +190,30 @@ int vlmfw_gemm_tn(const void* a, int32_t lda, const void* w, int32_t ldw, int32_
                   int32_t k, const float* bias, int32_t epi, int32_t act, void* out, int32_t ldo, const float* resid,
                   int32_t ldr, int32_t resid_mod, int32_t grp, int32_t grp_out, int32_t grp_off, int32_t block_n,
                   void* stream);
+/* The same kernel with LayerNorm folded around it, as the tower chains it: no LayerNorm kernel runs
+ * between GEMMs.
+ *  producer side (epi = VLMFW_EPI_BIAS_RESID_F32): besides out = acc + bias + resid, the epilogue stores the 16-bit cast
+ *    of the updated rows to h16_out [M, ld_h16] and, per row, `vlmfw_gemm_stats_parts(n, block_n)` float2 partials
+ *    (sum, sum of squares) to stats_out [M, parts];
+ *  consumer side (epi = VLMFW_EPI_BIAS_BF16): A is that plain 16-bit cast, W = round16(gamma . W) with every row
+ *    centred (the mean subtraction of LayerNorm is the projection I - 11^T/K, moved onto the weights) and
+ *    out = act(rstd[m] acc + bias[n]) with rstd from ln_stats [M, ln_np] over ln_dim columns;
+ *    W and bias = beta W^T + b come from vlmfw_ln_fold_weight.
+ * Fields left 0 / NULL switch the corresponding part off. */
+typedef struct vlmfw_gemm_desc {
+    const void* a; int32_t lda; const void* w; int32_t ldw; int32_t dtype; int32_t m, n, k;
+    const float* bias; int32_t epi, act; void* out; int32_t ldo; const float* resid; int32_t ldr; int32_t block_n;
+    const void* ln_stats; int32_t ln_np, ln_dim; float ln_eps;
+    void* h16_out; int32_t ld_h16; void* stats_out;
+} vlmfw_gemm_desc;
+int vlmfw_gemm_tn_ex(const vlmfw_gemm_desc* desc, void* stream);
+int32_t vlmfw_gemm_stats_parts(int32_t n, int32_t block_n);
+/* x fp32 [rows, dim] -> out16 = 16-bit cast (dtype), stats [rows, parts] float2 with (sum, sum of squares) in slot 0 */
+int vlmfw_row_stats_cast(const float* x, int32_t rows, int32_t dim, void* out16, int32_t dtype, void* stats,
+                         int32_t parts, void* stream);
+/* w fp32 [n, k] -> w16 [n, ld] = round16(gamma[k] w[n,k] - mean_j(gamma[j] w[n,j])); c2[n] = sum_k beta[k] w[n,k] + bias[n] */
+int vlmfw_ln_fold_weight(const float* w, int32_t n, int32_t k, const float* gamma, const float* beta, const float* bias,
+                         void* w16, int32_t ld, int32_t dtype, float* c2, void* stream);
 /* y = LayerNorm(x) * gamma + beta over rows of x [rows, dim] fp32; out_dtype VLMFW_DT_* (fp32 output may alias x) */
 int vlmfw_layernorm(const float* x, int32_t rows, int32_t dim, const float* gamma, const float* beta, float eps,
                     void* out, int32_t out_dtype, void* stream);

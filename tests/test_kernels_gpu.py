@@ -111,6 +111,96 @@ def test_gemm_residual_f32_out_of_place(cuda_device, form):
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-4)
 
 
+# ------------------------------------------------------------------ LayerNorm folded around the GEMMs
+@pytest.mark.parametrize("rows,dim,parts", [(37, 1152, 10), (4096, 1024, 8), (513, 1408, 12), (9, 144, 2)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_row_stats_cast(cuda_device, rows, dim, parts, dtype):
+    x = _rand((rows, dim), 40, 3.0) + 1.5
+    out, stats = ops.row_stats_cast(x, dtype=dtype, parts=parts)
+    assert torch.equal(out, x.to(dtype))  # round-to-nearest-even cast, bit exact
+    torch.testing.assert_close(stats[:, 0, 0], x.sum(1), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(stats[:, 0, 1], (x.double() ** 2).sum(1).float(), rtol=1e-5, atol=1e-3)
+    assert (stats[:, 1:] == 0).all()
+
+
+@pytest.mark.parametrize("n,k", [(3456, 1152), (4304, 1152), (432, 144), (4096, 1024)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_ln_fold_weight(cuda_device, n, k, dtype):
+    w = _rand((n, k), 41, 1 / math.sqrt(k))
+    gamma, beta, bias = 1 + _rand((k,), 42, 0.2), _rand((k,), 43, 0.2), _rand((n,), 44, 0.5)
+    w16, c2 = ops.ln_fold_weight(w, gamma, beta, bias, dtype=dtype)
+    gw = w.double() * gamma.double()
+    want = (gw - gw.mean(1, keepdim=True)).float()
+    # round-to-nearest of the centred row; the fp32 FMA of the kernel may differ from the fp64 restatement by one ulp
+    # of the 16-bit type on a rounding boundary, never more
+    ulp = 2.0 ** (-10 if dtype == torch.float16 else -7)
+    assert ((w16.float() - want).abs() <= ulp * want.abs().clamp_min(2.0 ** -14)).all()
+    assert (w16.float() == want.to(dtype).float()).float().mean() > 0.999
+    assert w16.double().sum(1).abs().max() < 0.05  # rows are centred up to the 16-bit rounding residue
+    torch.testing.assert_close(c2, (w.double() @ beta.double() + bias.double()).float(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("m,n,k", [(384, 1152, 1152), (1000, 3456, 1152), (520, 4304, 1152), (130, 432, 144),
+                                   (40, 176, 384), (20000, 1152, 1152)])
+@pytest.mark.parametrize("form", ["1cta", "2cta"])
+@pytest.mark.parametrize("act", [specs.ACT_NONE, specs.ACT_GELU_TANH])
+def test_gemm_folded_layernorm_consumer(cuda_device, m, n, k, form, act):
+    """LN(x) W^T + b through (row_stats_cast -> ln_fold_weight -> GEMM with the LN epilogue) == torch's layer_norm + linear."""
+    x = _rand((m, k), 45, 2.0) + 0.7  # rows with a non-zero mean: the mu c1 cancellation is exercised
+    w = _rand((n, k), 46, 1 / math.sqrt(k))
+    gamma, beta, bias = 1 + _rand((k,), 47, 0.2), _rand((k,), 48, 0.2), _rand((n,), 49, 0.5)
+    parts = 5
+    x16, stats = ops.row_stats_cast(x, dtype=torch.float16, parts=parts)
+    w16, c2 = ops.ln_fold_weight(w, gamma, beta, bias, dtype=torch.float16)
+    out = ops.gemm_tn_ln(x16, w16, c2, stats, k, 1e-6, act=act, block_n=FORMS[form])
+    ref = _act_ref(torch.nn.functional.layer_norm(x, (k,), gamma, beta, 1e-6) @ w.t() + bias, act)
+    # same error budget as the unfused path (fp16 operands, fp32 accumulate, fp16 output)
+    torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+    # and against the unfused kernels on the same inputs: the fold must not cost accuracy
+    xn = ops.layernorm(x, gamma, beta, 1e-6, dtype=torch.float16)
+    unfused = ops.gemm_tn(xn, w.to(torch.float16), bias, act=act, block_n=FORMS[form])
+    err_fused = (out.float() - ref).abs().max().item()
+    err_unfused = (unfused.float() - ref).abs().max().item()
+    assert err_fused <= 2.0 * err_unfused + 2e-3, (err_fused, err_unfused)
+
+
+@pytest.mark.parametrize("m,n,k", [(384, 1152, 1152), (777, 1152, 4304), (130, 144, 304), (64, 1408, 6144),
+                                   (20000, 1024, 1024)])
+@pytest.mark.parametrize("form", ["1cta", "2cta"])
+@pytest.mark.parametrize("block_n", [0, 128, 192, 256])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_gemm_residual_producer_stats_and_cast(cuda_device, m, n, k, form, block_n, dtype):
+    a = _rand((m, k), 50).to(dtype)
+    w = _rand((n, k), 51, 1 / math.sqrt(k)).to(dtype)
+    bias = _rand((n,), 52, 0.5)
+    h = _rand((m, n), 53, 2.0) + 0.5
+    ref = a.float() @ w.float().t() + bias + h
+    h16, stats = ops.gemm_tn_resid_stats(a, w, bias, h, block_n=block_n | FORMS[form])
+    torch.testing.assert_close(h, ref, rtol=1e-4, atol=2e-4)
+    assert torch.equal(h16, h.to(dtype))  # the cast of exactly what was stored
+    assert not torch.isnan(stats).any()  # every partial slot written
+    tot = stats.sum(1)
+    torch.testing.assert_close(tot[:, 0], h.sum(1), rtol=1e-4, atol=2e-2)
+    torch.testing.assert_close(tot[:, 1], (h * h).sum(1), rtol=1e-4, atol=2e-2)
+
+
+def test_gemm_folded_chain_matches_layernorm_linear(cuda_device):
+    """producer -> consumer exactly as the tower chains them: h += a W_o^T + b_o; y = LN(h) W_1^T + b_1."""
+    m, d, i = 3000, 1152, 4304
+    a = _rand((m, d), 54).to(torch.float16)
+    wo = _rand((d, d), 55, 1 / math.sqrt(d)).to(torch.float16)
+    bo = _rand((d,), 56, 0.5)
+    h = _rand((m, d), 57, 2.0)
+    w1 = _rand((i, d), 58, 1 / math.sqrt(d))
+    gamma, beta, b1 = 1 + _rand((d,), 59, 0.2), _rand((d,), 60, 0.2), _rand((i,), 61, 0.5)
+    href = a.float() @ wo.float().t() + bo + h
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(href, (d,), gamma, beta, 1e-6) @ w1.t() + b1, approximate="tanh")
+    h16, stats = ops.gemm_tn_resid_stats(a, wo, bo, h)
+    w16, c2 = ops.ln_fold_weight(w1, gamma, beta, b1)
+    out = ops.gemm_tn_ln(h16, w16, c2, stats, d, 1e-6, act=specs.ACT_GELU_TANH)
+    torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+
+
 def test_gemm_rejects_bad_arguments(cuda_device):
     from vlmfw_b200._lib import VlmfwError
 

@@ -46,6 +46,17 @@ class Head(C.Structure):
 
 _vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
+
+class GemmDesc(C.Structure):
+    """``vlmfw_gemm_desc``: the GEMM with LayerNorm folded around it (producer / consumer sides, see the header)."""
+    _fields_ = [
+        ("a", _vp), ("lda", _i32), ("w", _vp), ("ldw", _i32), ("dtype", _i32), ("m", _i32), ("n", _i32), ("k", _i32),
+        ("bias", _vp), ("epi", _i32), ("act", _i32), ("out", _vp), ("ldo", _i32), ("resid", _vp), ("ldr", _i32),
+        ("block_n", _i32), ("ln_stats", _vp), ("ln_np", _i32), ("ln_dim", _i32), ("ln_eps", _f32),
+        ("h16_out", _vp), ("ld_h16", _i32), ("stats_out", _vp),
+    ]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/vlmfw_b200.h
 SIGNATURES = {
     "vlmfw_abi_version": (C.c_int, []),
@@ -69,6 +80,10 @@ SIGNATURES = {
     "vlmfw_probe_bn_running_update": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, _vp]),
     "vlmfw_gemm_tn": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
                                 _i32, _i32, _i32, _i32, _i32, _vp]),
+    "vlmfw_gemm_tn_ex": (C.c_int, [C.POINTER(GemmDesc), _vp]),
+    "vlmfw_gemm_stats_parts": (_i32, [_i32, _i32]),
+    "vlmfw_row_stats_cast": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "vlmfw_ln_fold_weight": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "vlmfw_layernorm": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _f32, _vp, _i32, _vp]),
     "vlmfw_attention": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "vlmfw_im2col": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), C.POINTER(_f32), _vp, _i32, _i32, _vp]),

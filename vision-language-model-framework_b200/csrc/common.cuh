@@ -55,6 +55,17 @@ struct GemmArgs {
     int resid_mod = 0;
     int grp = 0, grp_out = 0, grp_off = 0;
     int block_n = 0;  // 0 = pick automatically
+    // LayerNorm folded into this GEMM (16-bit epilogue): A is the plain 16-bit cast of the fp32 rows, W carries gamma
+    // and the mean subtraction (centred rows), bias carries beta W^T + b; ln_stats = [M][ln_np] float2 (sum, sum of
+    // squares) partials the epilogue turns into rstd
+    const void* ln_stats = nullptr;
+    int ln_np = 0, ln_dim = 0;
+    float ln_eps = 0.f;
+    // residual epilogue extras: 16-bit copy of the updated rows and their (sum, sum of squares) partials
+    // ([M][gemm_stats_parts(n, block_n)] float2) for the LayerNorm folded into the NEXT GEMM
+    void* h16_out = nullptr;
+    int ld_h16 = 0;
+    void* stats_out = nullptr;
     bool f16 = false;  // 16-bit format of A, W and the 16-bit output: false = bf16, true = fp16 (A and W must agree)
 };
 
@@ -66,8 +77,16 @@ int encode_tensor_map(CUtensorMap* out, bool f16, int rank, const void* ptr, con
 int device_check();
 int num_sms();
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
+// number of (sum, sum of squares) partials per row the residual epilogue writes for an N-column output
+int gemm_stats_parts(int n, int block_n);
 int launch_layernorm(const float* x, int rows, int dim, const float* gamma, const float* beta, float eps, void* out,
                      int out_dtype, cudaStream_t stream);
+// fp32 rows -> plain 16-bit cast + (sum, sum of squares) in partial slot 0 of stats [rows][np] float2 (others zeroed)
+int launch_row_stats_cast(const float* x, int rows, int dim, void* out16, bool f16, void* stats, int np,
+                          cudaStream_t stream);
+// W'[n,k] = round16(gamma[k] W[n,k] - mean_j(gamma[j] W[n,j])) (row stride ld), c2[n] = sum_k beta[k] W[n,k] + bias[n]
+int launch_ln_fold_weight(const float* w, int n, int k, const float* gamma, const float* beta, const float* bias,
+                          void* w16, int ld, bool f16, float* c2, cudaStream_t stream);
 int launch_attention(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out,
                      cudaStream_t stream);
 // tcgen05 attention (attention_tc.cu): 0 = launched, 1 = shape not covered (use launch_attention's generic kernel), <0 = error

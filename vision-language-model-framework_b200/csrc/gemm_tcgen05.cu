@@ -43,15 +43,12 @@ constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int STAGING_PER_WARP = 32 * 128;  // generic epilogue: 32 rows x 32 fp32
-#ifndef VLMFW_RES_NBUF
-#define VLMFW_RES_NBUF 2
-#endif
-#ifndef VLMFW_RES_COLS
-#define VLMFW_RES_COLS 32
-#endif
-constexpr int RES_NBUF = VLMFW_RES_NBUF;  // residual epilogue: ring of [32 rows x RES_COLS fp32] TMA boxes per warp
-constexpr int RES_COLS = VLMFW_RES_COLS;  // 32 (128B-swizzled boxes) or 16 (64B-swizzled)
-static_assert(RES_COLS == 16 || RES_COLS == 32, "residual box is 16 or 32 fp32 columns wide");
+// residual epilogue, per warp: ring of RES_NBUF [32 rows x RES_COLS fp32] TMA boxes (64B-swizzled) + one
+// [32 rows x 32 cols] 16-bit box for the fused cast of the updated residual stream (next GEMM's A operand)
+constexpr int RES_NBUF = 3;
+constexpr int RES_COLS = 16;
+constexpr int RES_BOX_BYTES = 32 * RES_COLS * 4;
+constexpr int H16_BOX_BYTES = 32 * 32 * 2;
 constexpr int SMEM_LIMIT = 232448;          // 227 KB opt-in maximum per CTA
 
 template <int BN, int CG, int EPI, bool GEN>
@@ -61,9 +58,9 @@ struct Cfg {
     static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // per-warp epilogue staging: generic 4 KB transpose buffer; 16-bit TMA-store path 2 x [32 x 64 B] boxes;
-    // residual path RES_NBUF x [32 x RES_COLS fp32] boxes
+    // residual path RES_NBUF x [32 x RES_COLS fp32] boxes + the 16-bit cast box
     static constexpr int STG_PER_WARP =
-        GEN ? STAGING_PER_WARP : (EPI == VLMFW_EPI_BIAS_RESID_F32 ? RES_NBUF * 32 * RES_COLS * 4 : 2 * 2048);
+        GEN ? STAGING_PER_WARP : (EPI == VLMFW_EPI_BIAS_RESID_F32 ? RES_NBUF * RES_BOX_BYTES + H16_BOX_BYTES : 2 * 2048);
     static constexpr int STAGING_BYTES = EPI_WARPS * STG_PER_WARP;
     static constexpr int BAR_BYTES = 512;
     static constexpr int RING_MAX = (SMEM_LIMIT - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
@@ -84,6 +81,17 @@ struct KParams {
     int ldr;
     int resid_mod;
     int grp, grp_out, grp_off;
+    // LayerNorm folded into the consumer (16-bit epilogue): out = act(rstd[m] acc + bias[n]); the weights carry gamma
+    // and the mean subtraction (rows centred: x (I - 11^T/K) W'^T == x (W' - rowmean(W'))^T), rstd comes from the
+    // (sum, sum of squares) partials the producer of A's fp32 source left in ln_stats
+    const float2* ln_stats;
+    int ln_np;
+    float ln_inv_dim, ln_eps;
+    // ... and its producer side (residual epilogue): 16-bit copy of the updated rows through tmap_h16 and per-row
+    // (sum, sum of squares) over this warp's 128 / 96 / 64 columns at stats_out[row * stats_np + 2 * n_tile + half]
+    float2* stats_out;
+    int stats_np;
+    int h16_on;
     int dbg;  // VLMFW_GEMM_DBG bit mask (bottleneck experiments only): 1 no TMA after the ring is primed, 2 no epilogue
               // global traffic, 4 no MMA issue
 };
@@ -91,12 +99,13 @@ struct KParams {
 template <int ACT>
 __device__ __forceinline__ float activation(float x) {
     if constexpr (ACT == VLMFW_ACT_GELU_TANH) {
-        // 0.5 x (1 + tanh(u)) == x * sigmoid(2u) = x / (1 + 2^(-2u log2 e)), u = sqrt(2/pi) (x + 0.044715 x^3)
-        // (activations.py gelu_pytorch_tanh); the constants are folded so the exponent costs FMUL + FFMA + FMUL
-        constexpr float B = -1.5957691216057308f * 1.4426950408889634f;  // -2 sqrt(2/pi) log2(e)
-        constexpr float A = B * 0.044715f;
-        const float e = ex2_approx(x * fmaf(x * x, A, B));
-        return __fdividef(x, 1.0f + e);
+        // 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3)   (activations.py gelu_pytorch_tanh)
+        // One MUFU (tanh.approx, |rel err| <= 2^-11: half the rounding step of the 16-bit output it feeds) and five
+        // FP32 ops; the sigmoid form needs two MUFUs and the SFU pipe is what paces this epilogue (ncu: 'mio' stalls).
+        constexpr float C0 = 0.7978845608028654f, C1 = 0.7978845608028654f * 0.044715f;
+        const float u = x * fmaf(x * x, C1, C0);
+        const float hx = 0.5f * x;
+        return fmaf(hx, tanh_approx(u), hx);
     } else if constexpr (ACT == VLMFW_ACT_QUICK_GELU) {
         // x * sigmoid(1.702 x)  (activations.py QuickGELU)
         return __fdividef(x, 1.0f + ex2_approx(x * (-1.702f * 1.4426950408889634f)));
@@ -111,7 +120,7 @@ template <int BN, int EPI, int ACT, int CG, bool GEN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                    const KParams p) {
+                    const __grid_constant__ CUtensorMap tmap_h16, const KParams p) {
     using C = Cfg<BN, CG, EPI, GEN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -287,6 +296,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
                 const int m0 = (tile / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
                 const int n0 = (tile % n_tiles) * BN + half * COLS_PER_WARP;
+                // folded LayerNorm: this thread's row statistics from the producer's partial sums (fixed order)
+                float mu = 0.f, rstd = 1.f;
+                if (p.ln_stats != nullptr && m0 + lane < p.m) {
+                    const float2* sp = p.ln_stats + static_cast<size_t>(m0 + lane) * p.ln_np;
+                    float s1 = 0.f, s2 = 0.f;
+                    for (int i = 0; i < p.ln_np; ++i) {
+                        const float2 t = __ldg(sp + i);
+                        s1 += t.x;
+                        s2 += t.y;
+                    }
+                    mu = s1 * p.ln_inv_dim;
+                    rstd = rsqrtf(fmaxf(s2 * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
+                }
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 uint32_t v[32];
@@ -300,10 +322,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int j = 0; j < 8; ++j) {
                         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (p.bias != nullptr && nc + 4 * j < p.n) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 4 * j));
-                        y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bv.x;
-                        y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv.y;
-                        y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv.z;
-                        y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv.w;
+                        y[4 * j + 0] = fmaf(rstd, __uint_as_float(v[4 * j + 0]), bv.x);
+                        y[4 * j + 1] = fmaf(rstd, __uint_as_float(v[4 * j + 1]), bv.y);
+                        y[4 * j + 2] = fmaf(rstd, __uint_as_float(v[4 * j + 2]), bv.z);
+                        y[4 * j + 3] = fmaf(rstd, __uint_as_float(v[4 * j + 3]), bv.w);
                     }
                     // the next chunk's TMEM read flies while this one is activated, packed and stored
                     if (c + 1 < CHUNKS) tmem_ld_32x32(lane_taddr + static_cast<uint32_t>(acc * BN + (c + 1) * 32), v);
@@ -339,14 +361,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (lane == 0) tma_store_wait_all();
         } else if constexpr (!GEN && EPI == VLMFW_EPI_BIAS_RESID_F32) {
             // ---- fp32 residual: out = acc + bias + resid, usually in place on the residual stream. The residual chunk
-            // [32 rows x RES_COLS fp32] arrives by TMA in a swizzled box (ring of RES_NBUF per warp, loads issued
-            // RES_NBUF - 1 chunks ahead, across tile boundaries), every thread updates its own row in place, and the
-            // same box is TMA-stored. Narrow boxes buy ring depth (HBM latency) without taking smem from the operand
-            // ring, which needs its stages more (measured: 5 stages beat 4 by 3-7 % on every residual GEMM).
+            // [32 rows x 16 fp32] arrives by TMA in a 64B-swizzled box (ring of RES_NBUF per warp, the next chunk's
+            // load issued as soon as its box is free, across tile boundaries), every thread updates its own row in
+            // place, and the same box is TMA-stored. Fused for the LayerNorm that follows in the tower: a 16-bit copy
+            // of the updated rows (TMA-stored from a second box every two chunks) and the row's (sum, sum of squares)
+            // over this warp's columns, so the next GEMM normalises in its epilogue and no LayerNorm kernel runs.
             constexpr int RCHUNKS = COLS_PER_WARP / RES_COLS;
-            constexpr uint32_t ROW_BYTES = RES_COLS * 4;
-            constexpr uint32_t BOX_BYTES = 32 * ROW_BYTES;
-            const uint32_t sw = (RES_COLS == 32) ? (static_cast<uint32_t>(lane) & 7u) : ((static_cast<uint32_t>(lane) >> 1) & 3u);
+            static_assert(RCHUNKS % 2 == 0, "the 16-bit box spans two residual chunks");
+            const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;  // SWIZZLE_64B
+            const uint32_t h16_u32 = stg_u32 + RES_NBUF * RES_BOX_BYTES;
             uint64_t* my_bar = res_bar + ew * RES_NBUF;
             const int my_tiles = worker < num_tiles ? (num_tiles - worker + num_workers - 1) / num_workers : 0;
             const uint32_t total_q = static_cast<uint32_t>(my_tiles) * RCHUNKS;
@@ -356,16 +379,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int cx = (t % n_tiles) * BN + half * COLS_PER_WARP + c * RES_COLS;
                 const int cy = (t / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
                 const uint32_t b = qq % RES_NBUF;
-                mbar_arrive_expect_tx(&my_bar[b], BOX_BYTES);
-                tma_load_2d(stg + b * BOX_BYTES, &tmap_res, &my_bar[b], cx, cy);
+                mbar_arrive_expect_tx(&my_bar[b], RES_BOX_BYTES);
+                tma_load_2d(stg + b * RES_BOX_BYTES, &tmap_res, &my_bar[b], cx, cy);
             };
             if (lane == 0 && !(p.dbg & 2)) {
                 for (uint32_t qq = 0; qq < RES_NBUF - 1 && qq < total_q; ++qq) issue_load(qq);
             }
+            static_assert(RES_NBUF >= 3, "ring: chunk q's store may still read its box while q + 1 is processed");
             uint32_t q = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
                 const int m0 = (tile / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
                 const int n0 = (tile % n_tiles) * BN + half * COLS_PER_WARP;
+                float s1 = 0.f, s2 = 0.f;
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
 #pragma unroll 1
@@ -373,12 +398,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (p.dbg & 2) continue;
                     const int nc = n0 + c * RES_COLS;
                     uint32_t v[RES_COLS];
-                    const uint32_t taddr = lane_taddr + static_cast<uint32_t>(acc * BN + c * RES_COLS);
-                    tmem_ld_row(taddr, v);
+                    tmem_ld_row(lane_taddr + static_cast<uint32_t>(acc * BN + c * RES_COLS), v);
                     const uint32_t b = q % RES_NBUF;
-                    const uint32_t box = stg_u32 + b * BOX_BYTES + static_cast<uint32_t>(lane) * ROW_BYTES;
+                    const uint32_t box = stg_u32 + b * RES_BOX_BYTES + static_cast<uint32_t>(lane) * (RES_COLS * 4);
                     mbar_wait(&my_bar[b], (q / RES_NBUF) & 1u);
                     tmem_ld_wait();
+                    uint32_t hp[RES_COLS / 2];
 #pragma unroll
                     for (uint32_t j = 0; j < RES_COLS / 4; ++j) {
                         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -396,18 +421,42 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r.x), "f"(r.y), "f"(r.z),
                                      "f"(r.w)
                                      : "memory");
+                        s1 += (r.x + r.y) + (r.z + r.w);
+                        s2 = fmaf(r.x, r.x, fmaf(r.y, r.y, fmaf(r.z, r.z, fmaf(r.w, r.w, s2))));
+                        hp[2 * j] = p.out_f16 ? pack_f16x2(r.x, r.y) : pack_bf16x2(r.x, r.y);
+                        hp[2 * j + 1] = p.out_f16 ? pack_f16x2(r.z, r.w) : pack_bf16x2(r.z, r.w);
+                    }
+                    if (p.h16_on) {
+                        // this chunk is 32 bytes of the 64-byte row of the 16-bit box: 16B slots 2 (c & 1) + {0, 1}
+                        const uint32_t hrow = h16_u32 + static_cast<uint32_t>(lane) * 64u;
+                        const uint32_t slot = static_cast<uint32_t>(c & 1) * 2u;
+#pragma unroll
+                        for (uint32_t j = 0; j < 2; ++j) {
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + (((slot + j) ^ sw) << 4)),
+                                         "r"(hp[4 * j]), "r"(hp[4 * j + 1]), "r"(hp[4 * j + 2]), "r"(hp[4 * j + 3])
+                                         : "memory");
+                        }
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&tmap_out, stg_u32 + b * BOX_BYTES, nc, m0);
+                        if (p.h16_on && (c & 1)) {  // its own, OLDER bulk group: the wait below then covers it
+                            tma_store_2d(&tmap_h16, h16_u32, nc - RES_COLS, m0);
+                            tma_store_commit();
+                        }
+                        tma_store_2d(&tmap_out, stg_u32 + b * RES_BOX_BYTES, nc, m0);
                         tma_store_commit();
-                        // the box of chunk q + NBUF - 1 is the one chunk q - 1 was stored from: that store (every bulk
-                        // group but the newest, or the newest too when the ring has two boxes) must have read it
-                        tma_store_wait_read<(RES_NBUF > 2) ? 1 : 0>();
+                        // every bulk group but the newest (this chunk's fp32 store) has read its box: the box chunk
+                        // q - 1 was stored from (= box (q + NBUF - 1) % NBUF) takes the load issued NBUF - 1 chunks
+                        // ahead, and the 16-bit box may be rewritten by the next chunk
+                        tma_store_wait_read<1>();
                         if (q + RES_NBUF - 1 < total_q) issue_load(q + RES_NBUF - 1);
                     }
                     __syncwarp();
+                }
+                if (p.stats_out != nullptr && m0 + lane < p.m && !(p.dbg & 2)) {
+                    p.stats_out[static_cast<size_t>(m0 + lane) * p.stats_np + (tile % n_tiles) * 2 + half] =
+                        make_float2(s1, s2);
                 }
                 release_acc();
             }
@@ -611,19 +660,24 @@ template <int BN, int EPI, int ACT, int CG, bool GEN>
 int launch_one(const GemmArgs& g, cudaStream_t stream) {
     using C = Cfg<BN, CG, EPI, GEN>;
     const MapDt dt16 = g.f16 ? MAP_F16 : MAP_BF16;
-    CUtensorMap ta, tw, tout, tres;
+    CUtensorMap ta, tw, tout, tres, th16;
     int rc = get_tensor_map(g.a, g.m, g.k, g.lda, BM, BK, dt16, 128, &ta);
     if (rc != VLMFW_OK) return rc;
     rc = get_tensor_map(g.w, g.n, g.k, g.ldw, C::B_ROWS, BK, dt16, 128, &tw);
     if (rc != VLMFW_OK) return rc;
     tout = ta;  // unused by the generic epilogue, but a kernel parameter must be a valid object
     tres = ta;
+    th16 = ta;
     if constexpr (!GEN) {
         if constexpr (EPI == VLMFW_EPI_BIAS_RESID_F32) {
             rc = get_tensor_map(g.out, g.m, g.n, g.ldo, 32, RES_COLS, MAP_F32, RES_COLS * 4, &tout);
             if (rc != VLMFW_OK) return rc;
             rc = get_tensor_map(g.resid, g.m, g.n, g.ldr, 32, RES_COLS, MAP_F32, RES_COLS * 4, &tres);
             if (rc != VLMFW_OK) return rc;
+            if (g.h16_out != nullptr) {
+                rc = get_tensor_map(g.h16_out, g.m, g.n, g.ld_h16, 32, 32, dt16, 64, &th16);
+                if (rc != VLMFW_OK) return rc;
+            }
         } else {
             rc = get_tensor_map(g.out, g.m, g.n, g.ldo, 32, 32, dt16, 64, &tout);
             if (rc != VLMFW_OK) return rc;
@@ -650,6 +704,13 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
     p.grp = g.grp;
     p.grp_out = g.grp_out;
     p.grp_off = g.grp_off;
+    p.ln_stats = reinterpret_cast<const float2*>(g.ln_stats);
+    p.ln_np = g.ln_np;
+    p.ln_inv_dim = g.ln_dim > 0 ? 1.0f / static_cast<float>(g.ln_dim) : 0.f;
+    p.ln_eps = g.ln_eps;
+    p.stats_out = reinterpret_cast<float2*>(g.stats_out);
+    p.stats_np = 2 * ((g.n + BN - 1) / BN);
+    p.h16_on = g.h16_out != nullptr ? 1 : 0;
     static const int dbg = []() {
         const char* e = getenv("VLMFW_GEMM_DBG");
         return e ? atoi(e) : 0;
@@ -674,9 +735,9 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        VLMFW_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tw, tout, tres, p));
+        VLMFW_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tw, tout, tres, th16, p));
     } else {
-        kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tw, tout, tres, p);
+        kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tw, tout, tres, th16, p);
     }
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
@@ -771,6 +832,12 @@ int encode_tensor_map(CUtensorMap* out, bool f16, int rank, const void* ptr, con
     return VLMFW_OK;
 }
 
+int gemm_stats_parts(int n, int block_n) {
+    const int bn_req = block_n & 0xFFF;
+    const int bn = bn_req > 0 ? bn_req : pick_block_n(n);
+    return 2 * ((n + bn - 1) / bn);
+}
+
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     VLMFW_REQUIRE(g.a && g.w && g.out, "gemm: null operand");
     VLMFW_REQUIRE(g.m > 0 && g.n > 0 && g.k > 0, "gemm: bad shape m=%d n=%d k=%d", g.m, g.n, g.k);
@@ -787,6 +854,19 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
         VLMFW_REQUIRE(g.epi == VLMFW_EPI_BIAS_BF16, "gemm: unknown epilogue %d", g.epi);
     }
     if (g.bias) VLMFW_REQUIRE((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+    const bool generic_epi = g.grp > 0 || g.resid_mod > 0 || (g.block_n & VLMFW_GEMM_FORCE_GENERIC_EPI);
+    if (g.ln_stats != nullptr) {
+        VLMFW_REQUIRE(g.epi == VLMFW_EPI_BIAS_BF16 && !generic_epi, "gemm: folded LayerNorm needs the 16-bit TMA epilogue");
+        VLMFW_REQUIRE(g.ln_np > 0 && g.ln_dim > 0, "gemm: folded LayerNorm needs ln_np / ln_dim");
+        VLMFW_REQUIRE((reinterpret_cast<uintptr_t>(g.ln_stats) & 7) == 0, "gemm: ln_stats must be 8-byte aligned");
+    }
+    if (g.stats_out != nullptr || g.h16_out != nullptr) {
+        VLMFW_REQUIRE(g.epi == VLMFW_EPI_BIAS_RESID_F32 && !generic_epi,
+                      "gemm: row statistics / 16-bit copy are produced by the TMA residual epilogue only");
+        if (g.h16_out != nullptr)
+            VLMFW_REQUIRE(g.ld_h16 >= g.n && g.ld_h16 % 8 == 0 && (reinterpret_cast<uintptr_t>(g.h16_out) & 15) == 0,
+                          "gemm: h16_out needs ld_h16 >= n, a multiple of 8, and 16-byte alignment");
+    }
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
     const int bn_req = g.block_n & 0xFFF;

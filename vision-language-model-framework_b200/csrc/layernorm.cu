@@ -72,12 +72,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // SigLIP: pooled[b, d] = mean_s ( (h[b,s,d] - mu_s) * rstd_s ) * gamma[d] + beta[d].
-// grid = (batch, col_slabs). Phase 1: warps compute per-token (mu, rstd) into smem (every slab CTA recomputes them —
-// the second read comes from L2). Phase 2: thread d accumulates its column over the tokens.
-__global__ void __launch_bounds__(256) pool_ln_mean_kernel(const float* __restrict__ h, int tokens, int dim,
-                                                           const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, float eps,
-                                                           float* __restrict__ pooled) {
+// One CTA (1024 threads) per image. Phase 1: warps compute per-token (mu, rstd) into smem. Phase 2: thread d accumulates
+// its column over the tokens — the image's 1.2 MB was just read by phase 1, so this second pass is served by L2 and
+// HBM sees each row once (the first version used one CTA per 256-column slab, each recomputing every token's
+// statistics: 4x the algorithmic DRAM reads in the round-1 ncu capture).
+__global__ void __launch_bounds__(1024) pool_ln_mean_kernel(const float* __restrict__ h, int tokens, int dim,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps,
+                                                            float* __restrict__ pooled) {
     extern __shared__ float2 stats[];  // [tokens] (mean, rstd)
     const int b = blockIdx.x;
     const float* hb = h + static_cast<size_t>(b) * tokens * dim;
@@ -109,13 +111,21 @@ __global__ void __launch_bounds__(256) pool_ln_mean_kernel(const float* __restri
         if (lane == 0) stats[s] = make_float2(mean, rstd);
     }
     __syncthreads();
-    const int d = blockIdx.y * blockDim.x + threadIdx.x;
-    if (d < dim) {
-        float acc = 0.f;
-        for (int s = 0; s < tokens; ++s) {
-            const float2 st = stats[s];
-            acc += (hb[static_cast<size_t>(s) * dim + d] - st.x) * st.y;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;  // four independent chains keep loads in flight
+        int s = 0;
+        for (; s + 4 <= tokens; s += 4) {
+            const float2 t0 = stats[s], t1 = stats[s + 1], t2 = stats[s + 2], t3 = stats[s + 3];
+            acc0 += (hb[static_cast<size_t>(s) * dim + d] - t0.x) * t0.y;
+            acc1 += (hb[static_cast<size_t>(s + 1) * dim + d] - t1.x) * t1.y;
+            acc2 += (hb[static_cast<size_t>(s + 2) * dim + d] - t2.x) * t2.y;
+            acc3 += (hb[static_cast<size_t>(s + 3) * dim + d] - t3.x) * t3.y;
         }
+        for (; s < tokens; ++s) {
+            const float2 st = stats[s];
+            acc0 += (hb[static_cast<size_t>(s) * dim + d] - st.x) * st.y;
+        }
+        const float acc = (acc0 + acc1) + (acc2 + acc3);
         pooled[static_cast<size_t>(b) * dim + d] = acc / static_cast<float>(tokens) * gamma[d] + beta[d];
     }
 }
@@ -190,7 +200,120 @@ __global__ void __launch_bounds__(128) pool_cls_ln2_kernel(const float* __restri
     }
 }
 
+// Entry of the folded-LayerNorm chain: the first LayerNorm of the tower has no GEMM epilogue in front
+// of it, so this kernel does what the residual epilogue does for every later one — a plain 16-bit cast of the fp32
+// rows (the next GEMM's A operand) and the row's (sum, sum of squares) in partial slot 0, the other slots zeroed.
+template <bool F16>
+__global__ void __launch_bounds__(256) row_stats_cast_kernel(const float* __restrict__ x, int rows, int dim,
+                                                             void* __restrict__ out16, float2* __restrict__ stats,
+                                                             int np) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int nchunks = dim >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * dim);
+    uint2* orow = reinterpret_cast<uint2*>(static_cast<uint16_t*>(out16) + static_cast<size_t>(warp) * dim);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        const int c = i * 32 + lane;
+        if (c < nchunks) {
+            const float4 v = xr[c];
+            s1 += (v.x + v.y) + (v.z + v.w);
+            s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+            uint2 o;
+            o.x = pack_16x2<F16>(v.x, v.y);
+            o.y = pack_16x2<F16>(v.z, v.w);
+            orow[c] = o;
+        }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane < np) stats[static_cast<size_t>(warp) * np + lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+}
+
+// LayerNorm folded into the weights of the GEMM that consumes it (one block per output row n). With P = I - 11^T/K
+// (the mean subtraction, a projection): LN(x) W^T + b = rstd (x P) (gamma . W)^T + (beta W^T + b)
+//                                                     = rstd x (P (gamma . W)^T) + c2, so
+//   W'[n,k] = round16(gamma[k] W[n,k] - mean_j(gamma[j] W[n,j]))   (rows centred: the tensor core subtracts the mean)
+//   c2[n]   = sum_k beta[k] W[n,k] + b[n]
+// and the consuming epilogue is a single FMA per element: act(rstd[m] acc + c2[n]).
+template <bool F16>
+__global__ void __launch_bounds__(256) ln_fold_weight_kernel(const float* __restrict__ w, int k, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ bias,
+                                                             uint16_t* __restrict__ w16, int ld, float* __restrict__ c2) {
+    const int n = blockIdx.x;
+    const float* wr = w + static_cast<size_t>(n) * k;
+    uint16_t* orow = w16 + static_cast<size_t>(n) * ld;
+    double a1 = 0.0, a2 = 0.0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const double wv = static_cast<double>(wr[i]);
+        a1 += wv * static_cast<double>(gamma[i]);
+        a2 += wv * static_cast<double>(beta[i]);
+    }
+    __shared__ double r1[8], r2[8];
+    __shared__ float row_mean;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        r1[threadIdx.x >> 5] = a1;
+        r2[threadIdx.x >> 5] = a2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int i = 0; i < 8; ++i) {
+            t1 += r1[i];
+            t2 += r2[i];
+        }
+        row_mean = static_cast<float>(t1 / static_cast<double>(k));
+        c2[n] = static_cast<float>(t2 + (bias != nullptr ? static_cast<double>(bias[n]) : 0.0));
+    }
+    __syncthreads();
+    const float mean = row_mean;
+    for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+        uint16_t bits = 0;
+        if (i < k) {
+            const float wf = fmaf(wr[i], gamma[i], -mean);
+            if constexpr (F16) bits = __half_as_ushort(__float2half_rn(wf));
+            else bits = __bfloat16_as_ushort(__float2bfloat16_rn(wf));
+        }
+        orow[i] = bits;
+    }
+}
+
 }  // namespace
+
+int launch_row_stats_cast(const float* x, int rows, int dim, void* out16, bool f16, void* stats, int np,
+                          cudaStream_t stream) {
+    VLMFW_REQUIRE(x && out16 && stats, "row_stats_cast: null pointer");
+    VLMFW_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAX_CHUNKS * 128, "row_stats_cast: bad dim %d", dim);
+    VLMFW_REQUIRE(np >= 1 && np <= 32, "row_stats_cast: %d partial slots (1..32)", np);
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    const int grid = (rows + 7) / 8;
+    if (f16) row_stats_cast_kernel<true><<<grid, 256, 0, stream>>>(x, rows, dim, out16, static_cast<float2*>(stats), np);
+    else row_stats_cast_kernel<false><<<grid, 256, 0, stream>>>(x, rows, dim, out16, static_cast<float2*>(stats), np);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+int launch_ln_fold_weight(const float* w, int n, int k, const float* gamma, const float* beta, const float* bias,
+                          void* w16, int ld, bool f16, float* c2, cudaStream_t stream) {
+    VLMFW_REQUIRE(w && gamma && beta && w16 && c2, "ln_fold_weight: null pointer");
+    VLMFW_REQUIRE(n > 0 && k > 0 && ld >= k, "ln_fold_weight: bad shape n=%d k=%d ld=%d", n, k, ld);
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    if (f16)
+        ln_fold_weight_kernel<true><<<n, 256, 0, stream>>>(w, k, gamma, beta, bias, static_cast<uint16_t*>(w16), ld, c2);
+    else
+        ln_fold_weight_kernel<false><<<n, 256, 0, stream>>>(w, k, gamma, beta, bias, static_cast<uint16_t*>(w16), ld, c2);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
 
 int launch_layernorm(const float* x, int rows, int dim, const float* gamma, const float* beta, float eps, void* out,
                      int out_dtype, cudaStream_t stream) {
@@ -227,8 +350,7 @@ int launch_pool(const float* h, int batch, int tokens, int dim, int pool, const 
         case VLMFW_POOL_LN_MEAN:
             VLMFW_REQUIRE(gamma && beta, "pool: LN_MEAN needs gamma/beta");
             VLMFW_REQUIRE(tokens * sizeof(float2) <= 48 * 1024, "pool: too many tokens %d", tokens);
-            pool_ln_mean_kernel<<<grid, threads, tokens * sizeof(float2), stream>>>(h, tokens, dim, gamma, beta, eps,
-                                                                                     pooled);
+            pool_ln_mean_kernel<<<batch, 1024, tokens * sizeof(float2), stream>>>(h, tokens, dim, gamma, beta, eps, pooled);
             break;
         case VLMFW_POOL_MEAN:
             pool_mean_kernel<<<grid, threads, 0, stream>>>(h, tokens, dim, tokens, pooled);

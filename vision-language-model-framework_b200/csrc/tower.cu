@@ -7,7 +7,10 @@
 // HBM layout per forward (M = B*S tokens), all inside one caller-provided workspace:
 //   h    fp32 [M, D]    residual stream — kept in fp32 end to end (bf16 residuals miss the
 //                       1e-2 logit tolerance); read by LayerNorm, read-modify-written by the out-proj / fc2 epilogues
-//   xn   16b  [M, D]    LayerNorm output = A operand of the QKV / fc1 GEMMs (16b = fp16 or bf16, cfg.compute_dtype)
+//   xn   16b  [M, D]    plain 16-bit cast of h = A operand of the QKV / fc1 GEMMs (16b = fp16 or bf16,
+//                       cfg.compute_dtype); written by the out-proj / fc2 epilogues, never by a LayerNorm kernel
+//   stats f32 [M, NP, 2] per-row (sum, sum of squares) partials of h from the same epilogues: LayerNorm itself is
+//                       folded into the QKV / fc1 GEMMs (gamma in the weights, mean / rstd applied in their epilogue)
 //   qkv  16b  [M, 3D]   fused projection, consumed in place by the attention kernel (no head permute)
 //   ctx  16b  [M, D]    attention output = A operand of out-proj
 //   mid  16b  [M, I]    GELU(fc1) = A operand of fc2; the patch-gather matrix [B*P, 592] aliases it before layer 0
@@ -89,6 +92,8 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Slot {
     void** dst = nullptr;
+    float** master = nullptr;  // matrices a LayerNorm is folded into keep their fp32 values: the 16-bit operand is
+                               // rebuilt from (W, gamma, beta, bias) whenever any of them changes (build_derived)
     bool matrix = false;  // repack to fp16 / bf16 [rows, ld]
     int64_t rows = 0, cols = 0, ld = 0;
     bool required = true;
@@ -98,7 +103,9 @@ struct Slot {
 struct LayerW {
     float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
     float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
-    void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+    void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;  // wqkv / w1 hold gamma-folded weights
+    float *wqkv32 = nullptr, *w132 = nullptr;                           // fp32 masters of the folded matrices
+    float *c2qkv = nullptr, *c2fc1 = nullptr;  // derived: beta W^T + b (ln_fold_weight_kernel)
 };
 
 }  // namespace
@@ -128,9 +135,10 @@ struct vlmfw_tower {
     size_t host_pooled_bytes = 0;
 
     void add_slot(const std::string& name, void** dst, bool matrix, int64_t rows, int64_t cols, int64_t ld,
-                  bool required = true) {
+                  bool required = true, float** master = nullptr) {
         Slot s;
         s.dst = dst;
+        s.master = master;
         s.matrix = matrix;
         s.rows = rows;
         s.cols = cols;
@@ -144,11 +152,13 @@ struct vlmfw_tower {
     size_t off_qkv(int B) const { return off_xn(B) + align_up(M(B) * D * 2, 1024); }
     size_t off_ctx(int B) const { return off_qkv(B) + align_up(M(B) * 3 * D * 2, 1024); }
     size_t off_mid(int B) const { return off_ctx(B) + align_up(M(B) * D * 2, 1024); }
-    size_t ws_bytes(int B) const {
+    size_t off_stats(int B) const {
         size_t mid = M(B) * I * 2;
         size_t pa = static_cast<size_t>(B) * P * kpad * 2;
         return off_mid(B) + align_up(mid > pa ? mid : pa, 1024);
     }
+    int stats_parts() const { return gemm_stats_parts(D, 0); }
+    size_t ws_bytes(int B) const { return off_stats(B) + align_up(M(B) * stats_parts() * 8, 1024); }
 };
 
 extern "C" int vlmfw_abi_version(void) { return VLMFW_ABI_VERSION; }
@@ -205,13 +215,13 @@ extern "C" int vlmfw_tower_create(const vlmfw_tower_cfg* cfg, vlmfw_tower** out)
         const std::string p = "L" + std::to_string(i) + ".";
         t->add_slot(p + "ln1.w", reinterpret_cast<void**>(&w.ln1w), false, 1, D, D);
         t->add_slot(p + "ln1.b", reinterpret_cast<void**>(&w.ln1b), false, 1, D, D);
-        t->add_slot(p + "qkv.w", &w.wqkv, true, 3 * D, D, D);
+        t->add_slot(p + "qkv.w", &w.wqkv, true, 3 * D, D, D, true, &w.wqkv32);
         t->add_slot(p + "qkv.b", reinterpret_cast<void**>(&w.bqkv), false, 1, 3 * D, 3 * D);
         t->add_slot(p + "o.w", &w.wo, true, D, D, D);
         t->add_slot(p + "o.b", reinterpret_cast<void**>(&w.bo), false, 1, D, D);
         t->add_slot(p + "ln2.w", reinterpret_cast<void**>(&w.ln2w), false, 1, D, D);
         t->add_slot(p + "ln2.b", reinterpret_cast<void**>(&w.ln2b), false, 1, D, D);
-        t->add_slot(p + "fc1.w", &w.w1, true, I, D, D);
+        t->add_slot(p + "fc1.w", &w.w1, true, I, D, D, true, &w.w132);
         t->add_slot(p + "fc1.b", reinterpret_cast<void**>(&w.b1), false, 1, I, I);
         t->add_slot(p + "fc2.w", &w.w2, true, D, I, I);
         t->add_slot(p + "fc2.b", reinterpret_cast<void**>(&w.b2), false, 1, D, D);
@@ -222,8 +232,13 @@ extern "C" int vlmfw_tower_create(const vlmfw_tower_cfg* cfg, vlmfw_tower** out)
 
 extern "C" void vlmfw_tower_destroy(vlmfw_tower* t) {
     if (!t) return;
-    for (auto& kv : t->slots)
+    for (auto& kv : t->slots) {
         if (*kv.second.dst) cudaFree(*kv.second.dst);
+        if (kv.second.master && *kv.second.master) cudaFree(*kv.second.master);
+    }
+    for (auto& w : t->layers)
+        for (float* ptr : {w.c2qkv, w.c2fc1})
+            if (ptr) cudaFree(ptr);
     if (t->posb) cudaFree(t->posb);
     if (t->cls_pos0) cudaFree(t->cls_pos0);
     if (t->host_pix_dev) cudaFree(t->host_pix_dev);
@@ -259,8 +274,14 @@ extern "C" int vlmfw_tower_set_weight(vlmfw_tower* t, const char* name, const fl
                 return VLMFW_E_RANGE;
             }
         }
-        int rc = launch_pack_16(src, s.rows, s.cols, *s.dst, s.ld, t->f16, st);
-        if (rc != VLMFW_OK) return rc;
+        if (s.master != nullptr) {
+            // LayerNorm-folded matrix: keep the fp32 values; build_derived() writes the 16-bit operand
+            if (*s.master == nullptr) VLMFW_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(s.master), static_cast<size_t>(numel) * 4));
+            VLMFW_CUDA_OK(cudaMemcpyAsync(*s.master, src, static_cast<size_t>(numel) * 4, cudaMemcpyDeviceToDevice, st));
+        } else {
+            int rc = launch_pack_16(src, s.rows, s.cols, *s.dst, s.ld, t->f16, st);
+            if (rc != VLMFW_OK) return rc;
+        }
     } else {
         VLMFW_CUDA_OK(cudaMemcpyAsync(*s.dst, src, static_cast<size_t>(numel) * 4, cudaMemcpyDeviceToDevice, st));
     }
@@ -301,6 +322,15 @@ static int build_derived(vlmfw_tower* t, cudaStream_t st) {
         rc = launch_add_rows(t->pos, t->cls, t->cls_pos0, 1, t->D, 0, st);
         if (rc != VLMFW_OK) return rc;
     }
+    // fold ln1 into the QKV projection and ln2 into fc1 (layernorm.cu: ln_fold_weight_kernel)
+    for (auto& w : t->layers) {
+        if (!w.c2qkv) VLMFW_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&w.c2qkv), static_cast<size_t>(3 * t->D) * 4));
+        if (!w.c2fc1) VLMFW_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&w.c2fc1), static_cast<size_t>(t->I) * 4));
+        rc = launch_ln_fold_weight(w.wqkv32, 3 * t->D, t->D, w.ln1w, w.ln1b, w.bqkv, w.wqkv, t->D, t->f16, w.c2qkv, st);
+        if (rc != VLMFW_OK) return rc;
+        rc = launch_ln_fold_weight(w.w132, t->I, t->D, w.ln2w, w.ln2b, w.b1, w.w1, t->D, t->f16, w.c2fc1, st);
+        if (rc != VLMFW_OK) return rc;
+    }
     t->derived_ok = true;
     return VLMFW_OK;
 }
@@ -327,6 +357,8 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
     void* qkv = ws + t->off_qkv(batch);
     void* ctx = ws + t->off_ctx(batch);
     void* mid = ws + t->off_mid(batch);
+    void* stats = ws + t->off_stats(batch);
+    const int np = t->stats_parts();
     void* patch_a = mid;
     const int D = t->D, I = t->I, S = t->S, P = t->P;
     const int M = batch * S;
@@ -366,11 +398,12 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         rc = launch_layernorm(h, M, D, t->pre_w, t->pre_b, t->cfg.ln_eps, h, VLMFW_DT_F32, st);
         if (rc != VLMFW_OK) return rc;
     }
-    // ---- encoder layers (pre-LN transformer blocks)
+    // ---- encoder layers (pre-LN transformer blocks). No LayerNorm kernel runs in here: ln1 / ln2 are folded into the
+    // QKV / fc1 GEMMs; the out-proj / fc2 epilogues leave the 16-bit copy of h (xn) and its row statistics behind.
+    rc = launch_row_stats_cast(h, M, D, xn, t->f16, stats, np, st);
+    if (rc != VLMFW_OK) return rc;
     for (int li = 0; li < t->L; ++li) {
         const LayerW& w = t->layers[li];
-        rc = launch_layernorm(h, M, D, w.ln1w, w.ln1b, t->cfg.ln_eps, xn, act_dt, st);
-        if (rc != VLMFW_OK) return rc;
         GemmArgs g;
         g.a = xn;
         g.lda = D;
@@ -380,7 +413,11 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.m = M;
         g.n = 3 * D;
         g.k = D;
-        g.bias = w.bqkv;
+        g.bias = w.c2qkv;
+        g.ln_stats = stats;
+        g.ln_np = np;
+        g.ln_dim = D;
+        g.ln_eps = t->cfg.ln_eps;
         g.epi = VLMFW_EPI_BIAS_BF16;
         g.act = VLMFW_ACT_NONE;
         g.out = qkv;
@@ -404,9 +441,10 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.ldo = D;
         g.resid = h;
         g.ldr = D;
+        g.h16_out = xn;
+        g.ld_h16 = D;
+        g.stats_out = stats;
         rc = launch_gemm(g, st);
-        if (rc != VLMFW_OK) return rc;
-        rc = launch_layernorm(h, M, D, w.ln2w, w.ln2b, t->cfg.ln_eps, xn, act_dt, st);
         if (rc != VLMFW_OK) return rc;
         g = GemmArgs();
         g.a = xn;
@@ -417,7 +455,11 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.m = M;
         g.n = I;
         g.k = D;
-        g.bias = w.b1;
+        g.bias = w.c2fc1;
+        g.ln_stats = stats;
+        g.ln_np = np;
+        g.ln_dim = D;
+        g.ln_eps = t->cfg.ln_eps;
         g.epi = VLMFW_EPI_BIAS_BF16;
         g.act = t->cfg.act;
         g.out = mid;
@@ -439,6 +481,11 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.ldo = D;
         g.resid = h;
         g.ldr = D;
+        if (li + 1 < t->L) {  // the last layer feeds the pooling kernel, which reads the fp32 rows
+            g.h16_out = xn;
+            g.ld_h16 = D;
+            g.stats_out = stats;
+        }
         rc = launch_gemm(g, st);
         if (rc != VLMFW_OK) return rc;
     }
@@ -516,6 +563,51 @@ extern "C" int vlmfw_gemm_tn(const void* a, int32_t lda, const void* w, int32_t 
     g.grp_off = grp_off;
     g.block_n = block_n;
     return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlmfw_gemm_tn_ex(const vlmfw_gemm_desc* d, void* stream) {
+    VLMFW_REQUIRE(d != nullptr, "gemm_ex: null descriptor");
+    VLMFW_REQUIRE(d->dtype == VLMFW_DT_BF16 || d->dtype == VLMFW_DT_F16, "gemm: dtype must be VLMFW_DT_BF16 or VLMFW_DT_F16");
+    GemmArgs g;
+    g.a = d->a;
+    g.lda = d->lda;
+    g.w = d->w;
+    g.ldw = d->ldw;
+    g.f16 = d->dtype == VLMFW_DT_F16;
+    g.m = d->m;
+    g.n = d->n;
+    g.k = d->k;
+    g.bias = d->bias;
+    g.epi = d->epi;
+    g.act = d->act;
+    g.out = d->out;
+    g.ldo = d->ldo;
+    g.resid = d->resid;
+    g.ldr = d->ldr;
+    g.block_n = d->block_n;
+    g.ln_stats = d->ln_stats;
+    g.ln_np = d->ln_np;
+    g.ln_dim = d->ln_dim;
+    g.ln_eps = d->ln_eps;
+    g.h16_out = d->h16_out;
+    g.ld_h16 = d->ld_h16;
+    g.stats_out = d->stats_out;
+    return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int32_t vlmfw_gemm_stats_parts(int32_t n, int32_t block_n) { return gemm_stats_parts(n, block_n); }
+
+extern "C" int vlmfw_row_stats_cast(const float* x, int32_t rows, int32_t dim, void* out16, int32_t dtype, void* stats,
+                                    int32_t parts, void* stream) {
+    VLMFW_REQUIRE(dtype == VLMFW_DT_BF16 || dtype == VLMFW_DT_F16, "row_stats_cast: dtype must be VLMFW_DT_BF16 or VLMFW_DT_F16");
+    return launch_row_stats_cast(x, rows, dim, out16, dtype == VLMFW_DT_F16, stats, parts, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlmfw_ln_fold_weight(const float* w, int32_t n, int32_t k, const float* gamma, const float* beta,
+                                    const float* bias, void* w16, int32_t ld, int32_t dtype, float* c2, void* stream) {
+    VLMFW_REQUIRE(dtype == VLMFW_DT_BF16 || dtype == VLMFW_DT_F16, "ln_fold_weight: dtype must be VLMFW_DT_BF16 or VLMFW_DT_F16");
+    return launch_ln_fold_weight(w, n, k, gamma, beta, bias, w16, ld, dtype == VLMFW_DT_F16, c2,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vlmfw_layernorm(const float* x, int32_t rows, int32_t dim, const float* gamma, const float* beta,

@@ -83,6 +83,74 @@ def gemm_tn(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
     return out
 
 
+def gemm_stats_parts(n: int, block_n: int = 0) -> int:
+    return int(_lib.load().vlmfw_gemm_stats_parts(n, block_n))
+
+
+def row_stats_cast(x: torch.Tensor, dtype: torch.dtype = torch.float16, parts: int = 1):
+    """fp32 rows -> (16-bit cast, stats [rows, parts, 2] with (sum, sum of squares) in slot 0): head of the folded-LN chain."""
+    _need(x, torch.float32, "x")
+    rows, dim = x.shape
+    out = torch.empty(rows, dim, dtype=dtype, device=x.device)
+    stats = torch.empty(rows, parts, 2, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().vlmfw_row_stats_cast(x.data_ptr(), rows, dim, out.data_ptr(), _dt(out, "out"),
+                                                   stats.data_ptr(), parts, _st(x)))
+    return out, stats
+
+
+def ln_fold_weight(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                   dtype: torch.dtype = torch.float16):
+    """(W, LN gamma / beta, bias) -> (W' = round16(gamma . W with centred rows), c2 = W beta + bias)."""
+    _need(w, torch.float32, "w")
+    n, k = w.shape
+    w16 = torch.empty(n, k, dtype=dtype, device=w.device)
+    c2 = torch.empty(n, dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().vlmfw_ln_fold_weight(w.data_ptr(), n, k, gamma.data_ptr(), beta.data_ptr(),
+                                                   None if bias is None else bias.data_ptr(), w16.data_ptr(), k,
+                                                   _dt(w16, "w16"), c2.data_ptr(), _st(w)))
+    return w16, c2
+
+
+def gemm_tn_ln(a16: torch.Tensor, w16: torch.Tensor, c2: torch.Tensor, stats: torch.Tensor,
+               ln_dim: int, eps: float, *, act: int = ACT_NONE, block_n: int = 0) -> torch.Tensor:
+    """Consumer side of the folded LayerNorm: ``act(rstd (a16 @ w16^T) + c2)`` in a16's dtype."""
+    _need(a16, a16.dtype, "a16")
+    _need(w16, a16.dtype, "w16")
+    _need(stats, torch.float32, "stats")
+    m, k = a16.shape
+    n = w16.shape[0]
+    out = torch.empty(m, n, dtype=a16.dtype, device=a16.device)
+    d = _lib.GemmDesc(a=a16.data_ptr(), lda=k, w=w16.data_ptr(), ldw=k, dtype=_dt(a16, "a16"), m=m, n=n, k=k,
+                      bias=c2.data_ptr(), epi=EPI_BIAS_BF16, act=act, out=out.data_ptr(), ldo=n, resid=None, ldr=0,
+                      block_n=block_n, ln_stats=stats.data_ptr(), ln_np=stats.shape[1],
+                      ln_dim=ln_dim, ln_eps=eps, h16_out=None, ld_h16=0, stats_out=None)
+    with torch.cuda.device(a16.device):
+        _lib.check(_lib.load().vlmfw_gemm_tn_ex(C.byref(d), _st(a16)))
+    return out
+
+
+def gemm_tn_resid_stats(a16: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tensor], h: torch.Tensor, *,
+                        block_n: int = 0):
+    """Producer side: ``h += a16 @ w16^T + bias`` in place, returning (16-bit cast of the new h, stats [M, parts, 2])."""
+    _need(a16, a16.dtype, "a16")
+    _need(w16, a16.dtype, "w16")
+    _need(h, torch.float32, "h")
+    m, k = a16.shape
+    n = w16.shape[0]
+    parts = gemm_stats_parts(n, block_n)
+    h16 = torch.empty(m, n, dtype=a16.dtype, device=a16.device)
+    stats = torch.full((m, parts, 2), float("nan"), dtype=torch.float32, device=a16.device)
+    d = _lib.GemmDesc(a=a16.data_ptr(), lda=k, w=w16.data_ptr(), ldw=k, dtype=_dt(a16, "a16"), m=m, n=n, k=k,
+                      bias=None if bias is None else bias.data_ptr(), epi=EPI_BIAS_RESID_F32, act=ACT_NONE,
+                      out=h.data_ptr(), ldo=n, resid=h.data_ptr(), ldr=n, block_n=block_n, ln_stats=None,
+                      ln_np=0, ln_dim=0, ln_eps=0.0, h16_out=h16.data_ptr(), ld_h16=n, stats_out=stats.data_ptr())
+    with torch.cuda.device(a16.device):
+        _lib.check(_lib.load().vlmfw_gemm_tn_ex(C.byref(d), _st(a16)))
+    return h16, stats
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
               dtype: torch.dtype = torch.float16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need(x, torch.float32, "x")
