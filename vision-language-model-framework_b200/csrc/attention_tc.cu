@@ -2,15 +2,21 @@
 // Restates hf integrations/sdpa_attention.py:92 as called from modeling_siglip.py:285-309, modeling_clip.py:310-334 and
 // modeling_blip_2.py:328-351 — same contract and layouts as attention.cu (qkv [B*S, 3D] in, ctx [B*S, D] out).
 //
-// Persistent, warp-specialised, one CTA per SM (384 threads); a work item = (image, head, PAIR of 128-query blocks):
-//   warp 0       TMA loader  — 5-D tensor map over qkv (head_dim, head, q|k|v, token, image): out-of-range head_dim
-//                              columns and tokens past S arrive as zeros, so head_dim 72 / 88 need no padding in HBM
-//   warp 1       MMA issuer  — S_qb = Q_qb K_j^T (tcgen05.mma 128x128xdh, accumulator in TMEM), O_qb += P_qb V_j
-//                              (128 x dh x 128, V read MN-major straight from the token-major tile, no transpose)
-//   warps 4..7   softmax of query block 0, warps 8..11 of query block 1 (one thread = one query row = one TMEM lane):
-//                tcgen05.ld the 128 scores, row max / exp2 / row sum in registers with no shuffles, P -> fp16/bf16 ->
-//                128B-swizzled smem as the A operand of the P·V MMA. The two blocks ping-pong so the tensor pipe works
-//                on one while the SFUs exponentiate the other; both share every K/V tile.
+// Persistent, warp-specialised, TWO CTAs per SM (192 threads, 256 TMEM columns and ~100 KB of shared memory each); a
+// work item = (image, head, one block of 128 queries), keys in blocks of 64:
+//   warp 0       TMA loader  — 5-D tensor maps over qkv (head_dim, head, q|k|v, token, image): out-of-range head_dim
+//                              columns and tokens past S arrive as zeros, so head_dim 72 / 88 need no padding in HBM;
+//                              Q tile + 2-deep rings of K and V tiles, running ahead across items
+//   warp 1       MMA issuer  — S_j = Q K_j^T (tcgen05.mma 128 x 64 x dh into one of TWO score buffers in TMEM) and
+//                              O += P_j V_j (128 x dh x 64, V read MN-major straight from the token-major tile); the
+//                              scores of block j+1 are issued before P·V of block j, across item boundaries too
+//   warps 2..5   softmax     — one thread = one query row = one TMEM lane: tcgen05.ld the 64 scores, row max / exp2 /
+//                              row sum in registers with no shuffles, P -> fp16/bf16 -> one of TWO 128B-swizzled smem
+//                              tiles (the A operand of P·V); then the item's epilogue O / l -> ctx
+// The first version paired two query blocks in one 384-thread CTA per SM with 128-key blocks: its ncu capture showed
+// 13.5 % tensor-pipe activity and memory, SFU and MMA phases adding up instead of overlapping (0.31 ms where each of
+// the three alone is ~0.1 ms at SigLIP B=256) — one short dependent chain per SM. Two independent CTAs per SM with
+// double-buffered S and P give the SM four things to interleave.
 // O accumulates in TMEM across key blocks. The running max is only raised when it grows by more than 2^8 (exact: the
 // same reference max divides numerator and denominator); then O is rescaled in TMEM by the softmax warps.
 // head_dim = 64 + tail (0 / 8->16 / 24->32 columns): the tail lives in its own narrow 32B / 64B-swizzled tile and is
@@ -25,68 +31,92 @@
 namespace vlmfw {
 namespace {
 
-constexpr int TC_THREADS = 384;  // 3 warpgroups: {loader, MMA, 2 idle} + softmax(q block 0) + softmax(q block 1)
-constexpr int BLK = 128;  // query rows per block (= TMEM lanes) and keys per block
+constexpr int TC_THREADS = 192;  // loader warp, MMA warp, 4 softmax warps (TMEM lane quarter = warp % 4)
+constexpr int QB = 128;          // query rows per item (= TMEM lanes)
+constexpr int KB = 64;           // keys per block
+constexpr int NKV = 2;           // K / V ring depth
 
 template <int DH>
 struct TcCfg {
     static constexpr int TAIL = DH == 64 ? 0 : (DH == 72 ? 16 : 32);  // columns of the second head_dim group (zero padded)
     static constexpr int DHP = 64 + TAIL;
-    static constexpr int TAIL_ROW = TAIL * 2;                 // bytes per row of the tail tile (= its swizzle span)
+    static constexpr int TAIL_ROW = TAIL * 2;                      // bytes per row of the tail tile (= its swizzle span)
     static constexpr uint32_t TAIL_LAYOUT = TAIL == 16 ? 6u : 4u;  // SWIZZLE_32B : SWIZZLE_64B
-    static constexpr int MAIN_BYTES = BLK * 128;
-    static constexpr int TAIL_BYTES = BLK * TAIL_ROW;
-    static constexpr int TILE_BYTES = MAIN_BYTES + TAIL_BYTES;
-    static constexpr int P_BYTES = BLK * BLK * 2;
-    static constexpr int BAR_BYTES = 512;
-    static constexpr int SMEM_BYTES = 6 * TILE_BYTES + 2 * P_BYTES + BAR_BYTES + 1024;
+    static constexpr int Q_MAIN = QB * 128;
+    static constexpr int Q_BYTES = Q_MAIN + QB * TAIL_ROW;
+    static constexpr int KV_MAIN = KB * 128;
+    static constexpr int KV_BYTES = KV_MAIN + KB * TAIL_ROW;
+    static constexpr int P_BYTES = QB * KB * 2;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = Q_BYTES + 2 * NKV * KV_BYTES + 2 * P_BYTES + BAR_BYTES + 1024;
+    static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two CTAs must fit one SM's shared memory");
 };
 
 struct TcParams {
     void* out;
     int S, H, B, D;
-    int nqp;        // query-block pairs per (image, head)
+    int nq;         // query blocks per (image, head)
     int J;          // key blocks per (image, head)
-    int num_items;  // B * H * nqp
+    int num_items;  // B * H * nq
     float scale_log2;
     int f16;
-    int dbg;  // VLMFW_ATTN_DBG bit mask (bottleneck experiments only): 1 skip exp+P store, 2 skip P·V MMAs, 4 skip S MMAs, 8 skip max
+    int dbg;  // VLMFW_ATTN_DBG bit mask (bottleneck experiments only): 1 skip exp+P store, 2 skip P·V MMAs, 4 skip S MMAs
 };
 
-// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512)
-constexpr uint32_t TM_S = 0, TM_O = 256, TM_STRIDE = 128;
+// TMEM columns (256 allocated per CTA): S0 [0,64) S1 [64,128) O [128, 128 + DHP)
+constexpr uint32_t TM_S = 0, TM_O = 128;
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 
 template <int DH>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_constant__ CUtensorMap map_tail,
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qt,
+                    const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_kvt,
                     const TcParams p) {
     using C = TcCfg<DH>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                       // [2][TILE]
-    uint8_t* sK = sQ + 2 * C::TILE_BYTES;     // [2][TILE]
-    uint8_t* sV = sK + 2 * C::TILE_BYTES;     // [2][TILE]
-    uint8_t* sP = sV + 2 * C::TILE_BYTES;     // [2][P]
+    uint8_t* sQ = smem;                         // [Q_BYTES]
+    uint8_t* sK = sQ + C::Q_BYTES;              // [NKV][KV_BYTES]
+    uint8_t* sV = sK + NKV * C::KV_BYTES;       // [NKV][KV_BYTES]
+    uint8_t* sP = sV + NKV * C::KV_BYTES;       // [2][P_BYTES]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * C::P_BYTES);
     uint64_t* q_full = bars + 0;
     uint64_t* q_empty = bars + 1;
-    uint64_t* k_full = bars + 2;    // [2]
-    uint64_t* k_empty = bars + 4;   // [2]
-    uint64_t* v_full = bars + 6;    // [2]
-    uint64_t* v_empty = bars + 8;   // [2]
-    uint64_t* s_full = bars + 10;   // [2] per query block
+    uint64_t* k_full = bars + 2;    // [NKV]
+    uint64_t* k_empty = bars + 4;   // [NKV]
+    uint64_t* v_full = bars + 6;    // [NKV]
+    uint64_t* v_empty = bars + 8;   // [NKV]
+    uint64_t* s_full = bars + 10;   // [2] score buffers
     uint64_t* s_empty = bars + 12;  // [2]
-    uint64_t* p_full = bars + 14;   // [2]
-    uint64_t* pv_done = bars + 16;  // [2]
-    uint64_t* o_empty = bars + 18;  // [2]
+    uint64_t* p_full = bars + 14;   // [2] probability tiles
+    uint64_t* p_empty = bars + 16;  // [2] (= P·V of that block complete: P free, O updated)
+    uint64_t* o_full = bars + 18;
+    uint64_t* o_empty = bars + 19;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&map_main);
-        if (C::TAIL) tma_prefetch_desc(&map_tail);
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_kv);
+        if (C::TAIL) {
+            tma_prefetch_desc(&map_qt);
+            tma_prefetch_desc(&map_kvt);
+        }
         mbar_init(q_full, 1);
         mbar_init(q_empty, 1);
         for (int i = 0; i < 2; ++i) {
@@ -97,13 +127,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
             mbar_init(&s_full[i], 1);
             mbar_init(&s_empty[i], 4);
             mbar_init(&p_full[i], 4);
-            mbar_init(&pv_done[i], 1);
-            mbar_init(&o_empty[i], 4);
+            mbar_init(&p_empty[i], 1);
         }
+        mbar_init(o_full, 1);
+        mbar_init(o_empty, 4);
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, 256);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -111,39 +142,50 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int J = p.J;
+    const int n_local = static_cast<int>(blockIdx.x) < p.num_items
+                            ? (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                  static_cast<int>(gridDim.x)
+                            : 0;
 
-    // Register rebalancing (setmaxnreg works per warpgroup, inside the 384 x 168 registers the CTA was launched with:
-    // 128 x 56 + 256 x 224 = 64512): the producer warpgroup needs a handful of registers, a
-    // softmax thread keeps one full 128-score row (+ the O row in the epilogue) in registers.
-    if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------ TMA loader
+        // One in-order stream in CONSUMPTION order: the MMA warp issues the scores of block s before P·V of block
+        // s - 1, so K runs one block ahead of V — a V slot that frees late (after its P·V) never holds up a K load.
         if (lane == 0) {
-            int it = 0, g = 0;
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-                const int qp = item % p.nqp;
-                const int h = (item / p.nqp) % p.H;
-                const int b = item / (p.nqp * p.H);
-                const int nqb = ((qp * 2 + 1) * BLK < p.S) ? 2 : 1;  // the odd last query block has no partner
-                mbar_wait(q_empty, (it & 1) ^ 1);
-                mbar_arrive_expect_tx(q_full, nqb * C::TILE_BYTES);
-                for (int qb = 0; qb < nqb; ++qb) {
-                    const int tok0 = (qp * 2 + qb) * BLK;
-                    tma_load_5d(sQ + qb * C::TILE_BYTES, &map_main, q_full, 0, h, 0, tok0, b);
-                    if (C::TAIL) tma_load_5d(sQ + qb * C::TILE_BYTES + C::MAIN_BYTES, &map_tail, q_full, 64, h, 0, tok0, b);
+            const int T = n_local * J;
+            auto coords = [&](int s, int& b, int& h, int& j, int& qb) {
+                const int k = s / J;
+                j = s - k * J;
+                const int item = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
+                qb = item % p.nq;
+                h = (item / p.nq) % p.H;
+                b = item / (p.nq * p.H);
+            };
+            for (int s = 0; s <= T; ++s) {
+                int b, h, j, qb;
+                if (s < T) {
+                    coords(s, b, h, j, qb);
+                    if (j == 0) {
+                        const int k = s / J;
+                        mbar_wait(q_empty, (k & 1) ^ 1);
+                        mbar_arrive_expect_tx(q_full, C::Q_BYTES);
+                        tma_load_5d(sQ, &map_q, q_full, 0, h, 0, qb * QB, b);
+                        if (C::TAIL) tma_load_5d(sQ + C::Q_MAIN, &map_qt, q_full, 64, h, 0, qb * QB, b);
+                    }
+                    const int st = s % NKV;
+                    mbar_wait(&k_empty[st], ((s / NKV) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&k_full[st], C::KV_BYTES);
+                    tma_load_5d(sK + st * C::KV_BYTES, &map_kv, &k_full[st], 0, h, 1, j * KB, b);
+                    if (C::TAIL) tma_load_5d(sK + st * C::KV_BYTES + C::KV_MAIN, &map_kvt, &k_full[st], 64, h, 1, j * KB, b);
                 }
-                for (int j = 0; j < J; ++j, ++g) {
-                    const int st = g & 1;
-                    const uint32_t ph = (g >> 1) & 1;
-                    mbar_wait(&k_empty[st], ph ^ 1);
-                    mbar_arrive_expect_tx(&k_full[st], C::TILE_BYTES);
-                    tma_load_5d(sK + st * C::TILE_BYTES, &map_main, &k_full[st], 0, h, 1, j * BLK, b);
-                    if (C::TAIL) tma_load_5d(sK + st * C::TILE_BYTES + C::MAIN_BYTES, &map_tail, &k_full[st], 64, h, 1, j * BLK, b);
-                    mbar_wait(&v_empty[st], ph ^ 1);
-                    mbar_arrive_expect_tx(&v_full[st], C::TILE_BYTES);
-                    tma_load_5d(sV + st * C::TILE_BYTES, &map_main, &v_full[st], 0, h, 2, j * BLK, b);
-                    if (C::TAIL) tma_load_5d(sV + st * C::TILE_BYTES + C::MAIN_BYTES, &map_tail, &v_full[st], 64, h, 2, j * BLK, b);
+                if (s >= 1) {
+                    const int sv = s - 1;
+                    coords(sv, b, h, j, qb);
+                    const int st = sv % NKV;
+                    mbar_wait(&v_empty[st], ((sv / NKV) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&v_full[st], C::KV_BYTES);
+                    tma_load_5d(sV + st * C::KV_BYTES, &map_kv, &v_full[st], 0, h, 2, j * KB, b);
+                    if (C::TAIL) tma_load_5d(sV + st * C::KV_BYTES + C::KV_MAIN, &map_kvt, &v_full[st], 64, h, 2, j * KB, b);
                 }
             }
         }
@@ -151,193 +193,165 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
         // ------------------------------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const bool f16 = p.f16 != 0;
-            const uint32_t idesc_pv = umma_idesc_16_bmn(BLK, 64, f16);
-            const uint32_t idesc_pvt = umma_idesc_16_bmn(BLK, C::TAIL ? C::TAIL : 16, f16);
+            const uint32_t idesc_pv = umma_idesc_16_bmn(QB, 64, f16);
+            const uint32_t idesc_pvt = umma_idesc_16_bmn(QB, C::TAIL ? C::TAIL : 16, f16);
             const uint32_t q_u32 = smem_u32(sQ), k_u32 = smem_u32(sK), v_u32 = smem_u32(sV), p_u32 = smem_u32(sP);
-
-            // kcols = keys of this block rounded up to 32: the ragged last block (S = 257 -> 1 key, 577 -> 65) runs a
-            // narrower S MMA, fewer exponentials and fewer P·V K-steps instead of a full 128-key block
-            auto issue_s = [&](int qb, int st, int kcols) {
-                const uint32_t d = tmem_base + TM_S + qb * TM_STRIDE;
-                const uint32_t a0 = q_u32 + qb * C::TILE_BYTES, b0 = k_u32 + st * C::TILE_BYTES;
-                const uint64_t ad = umma_desc_sw128(a0), bd = umma_desc_sw128(b0);
-                const uint32_t idesc_s = umma_idesc_16(BLK, kcols, f16, f16);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(d, ad + 2 * ks, bd + 2 * ks, idesc_s, ks > 0 ? 1u : 0u);
-                if (C::TAIL) {
-                    const uint64_t at = umma_desc(a0 + C::MAIN_BYTES, 16, 8 * C::TAIL_ROW, C::TAIL_LAYOUT);
-                    const uint64_t bt = umma_desc(b0 + C::MAIN_BYTES, 16, 8 * C::TAIL_ROW, C::TAIL_LAYOUT);
-#pragma unroll
-                    for (int ks = 0; ks < C::TAIL / 16; ++ks) umma_bf16_ss(d, at + 2 * ks, bt + 2 * ks, idesc_s, 1u);
-                }
+            // keys of block j rounded up to the MMA's N granularity: the ragged last block (S = 257 -> 1 key,
+            // 577 -> 1 key) runs a 16-wide S MMA, 16 exponentials per row and one P·V K-step
+            auto kcols_of = [&](int j) {
+                const int valid = p.S - j * KB;
+                return valid >= KB ? KB : ((valid + 15) >> 4) << 4;
             };
-            auto issue_pv = [&](int qb, int st, bool acc, int kcols) {
-                const uint32_t d = tmem_base + TM_O + qb * TM_STRIDE;
-                const uint32_t a0 = p_u32 + qb * C::P_BYTES, b0 = v_u32 + st * C::TILE_BYTES;
-                const int ksteps = kcols >> 4;  // 16 keys per step
-#pragma unroll 1
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint64_t ad = umma_desc_sw128(a0 + (ks >> 2) * 16384) + 2 * (ks & 3);
-                    // V main tile: token-major rows of 128 B (64 head_dim columns) = MN-major SWIZZLE_128B operand;
-                    // 8-key groups are 1024 B apart, one K-step (16 keys) = 2048 B
-                    const uint64_t bd = umma_desc(b0 + ks * 2048, 16, 1024, 2);
-                    umma_bf16_ss(d, ad, bd, idesc_pv, (acc || ks > 0) ? 1u : 0u);
+            // The key blocks of all of this CTA's items form one stream t = 0 .. T-1 (item t / J, block t % J)
+            const int T = n_local * J;
+            auto issue_s = [&](int t) {
+                const int k = t / J, j = t - k * J, st = t % NKV, sb = t & 1;
+                if (j == 0) mbar_wait(q_full, k & 1);
+                mbar_wait(&k_full[st], (t / NKV) & 1);
+                mbar_wait(&s_empty[sb], ((t >> 1) & 1) ^ 1);
+                tc_fence_after();
+                if (!(p.dbg & 4)) {
+                    const uint32_t d = tmem_base + TM_S + sb * KB;
+                    const uint32_t b0 = k_u32 + st * C::KV_BYTES;
+                    const uint64_t ad = umma_desc_sw128(q_u32), bd = umma_desc_sw128(b0);
+                    const uint32_t idesc_s = umma_idesc_16(QB, kcols_of(j), f16, f16);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_bf16_ss(d, ad + 2 * ks, bd + 2 * ks, idesc_s, ks > 0 ? 1u : 0u);
                     if (C::TAIL) {
-                        const uint64_t bt = umma_desc(b0 + C::MAIN_BYTES + ks * 16 * C::TAIL_ROW, 16, 8 * C::TAIL_ROW,
-                                                      C::TAIL_LAYOUT);
-                        umma_bf16_ss(d + 64, ad, bt, idesc_pvt, (acc || ks > 0) ? 1u : 0u);
+                        const uint64_t at = umma_desc(q_u32 + C::Q_MAIN, 16, 8 * C::TAIL_ROW, C::TAIL_LAYOUT);
+                        const uint64_t bt = umma_desc(b0 + C::KV_MAIN, 16, 8 * C::TAIL_ROW, C::TAIL_LAYOUT);
+#pragma unroll
+                        for (int ks = 0; ks < C::TAIL / 16; ++ks) umma_bf16_ss(d, at + 2 * ks, bt + 2 * ks, idesc_s, 1u);
                     }
                 }
-            };
-            auto kcols_of = [&](int j) {
-                const int valid = p.S - j * BLK;
-                return valid >= BLK ? BLK : ((valid + 31) >> 5) << 5;
-            };
-            auto nqb_of = [&](int k) {
-                const int qp = (static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x)) % p.nqp;
-                return ((qp * 2 + 1) * BLK < p.S) ? 2 : 1;
-            };
-
-            // The key blocks of all of this CTA's items form one stream t = 0 .. T-1 (item t / J, block t % J): the
-            // scores of block t+1 are issued before P·V of block t — across item boundaries too — so the softmax warps
-            // always find their next S tile ready.
-            const int n_local = (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                                static_cast<int>(gridDim.x);
-            const int T = n_local * J;
-            uint32_t n[2] = {0, 0};    // S tiles issued per query block
-            uint32_t npv[2] = {0, 0};  // P·V blocks issued per query block
-            uint32_t itq[2] = {0, 0};  // items started per query block (o_empty phase)
-            auto issue_s_stage = [&](int t) {
-                const int k = t / J, j = t - k * J, st = t & 1;
-                if (j == 0) mbar_wait(q_full, k & 1);
-                mbar_wait(&k_full[st], (t >> 1) & 1);
-                const int nq = nqb_of(k), kcols = kcols_of(j);
-                for (int qb = 0; qb < nq; ++qb) {
-                    mbar_wait(&s_empty[qb], (n[qb] & 1) ^ 1);
-                    tc_fence_after();
-                    if (!(p.dbg & 4)) issue_s(qb, st, kcols);
-                    umma_commit(&s_full[qb]);
-                    ++n[qb];
-                }
+                umma_commit(&s_full[sb]);
                 umma_commit(&k_empty[st]);
                 if (j == J - 1) umma_commit(q_empty);
             };
-            if (T > 0) issue_s_stage(0);
-            for (int t = 0; t < T; ++t) {
-                const int k = t / J, j = t - k * J, st = t & 1;
-                // next block's scores go first, except across an item boundary: there they would wait for the next
-                // item's Q tile and hold up this item's last P·V (and with it the epilogue)
-                const bool s_first = j + 1 < J;
-                if (s_first && t + 1 < T) issue_s_stage(t + 1);
-                const int nq = nqb_of(k), kcols = kcols_of(j);
-                mbar_wait(&v_full[st], (t >> 1) & 1);
-                for (int qb = 0; qb < nq; ++qb) {
-                    mbar_wait(&p_full[qb], npv[qb] & 1);
-                    if (j == 0) {
-                        mbar_wait(&o_empty[qb], (itq[qb] & 1) ^ 1);
-                        ++itq[qb];
+            auto issue_pv = [&](int t) {
+                const int k = t / J, j = t - k * J, st = t % NKV, pb = t & 1;
+                mbar_wait(&v_full[st], (t / NKV) & 1);
+                mbar_wait(&p_full[pb], (t >> 1) & 1);
+                if (j == 0) mbar_wait(o_empty, (k & 1) ^ 1);
+                tc_fence_after();
+                if (!(p.dbg & 2)) {
+                    const uint32_t d = tmem_base + TM_O;
+                    const uint32_t a0 = p_u32 + pb * C::P_BYTES, b0 = v_u32 + st * C::KV_BYTES;
+                    const int ksteps = kcols_of(j) >> 4;  // 16 keys per step
+#pragma unroll 1
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t ad = umma_desc_sw128(a0) + 2 * ks;
+                        // V main tile: token-major rows of 128 B (64 head_dim columns) = MN-major SWIZZLE_128B operand;
+                        // 8-key groups are 1024 B apart, one K-step (16 keys) = 2048 B
+                        const uint64_t bd = umma_desc(b0 + ks * 2048, 16, 1024, 2);
+                        umma_bf16_ss(d, ad, bd, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+                        if (C::TAIL) {
+                            const uint64_t bt = umma_desc(b0 + C::KV_MAIN + ks * 16 * C::TAIL_ROW, 16, 8 * C::TAIL_ROW,
+                                                          C::TAIL_LAYOUT);
+                            umma_bf16_ss(d + 64, ad, bt, idesc_pvt, (j > 0 || ks > 0) ? 1u : 0u);
+                        }
                     }
-                    tc_fence_after();
-                    if (!(p.dbg & 2)) issue_pv(qb, st, j > 0, kcols);
-                    umma_commit(&pv_done[qb]);
-                    ++npv[qb];
                 }
+                umma_commit(&p_empty[pb]);
                 umma_commit(&v_empty[st]);
-                if (!s_first && t + 1 < T) issue_s_stage(t + 1);
+                if (j == J - 1) umma_commit(o_full);
+            };
+            if (T > 0) issue_s(0);
+            for (int t = 0; t < T; ++t) {
+                // next block's scores first (they keep the softmax warps fed) — unless that block opens the next item
+                // and its Q tile has not landed yet: then this item's P·V (and with it the epilogue) must not wait
+                bool s_first = t + 1 < T;
+                if (s_first && (t + 1) % J == 0) s_first = mbar_test(q_full, ((t + 1) / J) & 1);
+                if (s_first) issue_s(t + 1);
+                issue_pv(t);
+                if (!s_first && t + 1 < T) issue_s(t + 1);
             }
         }
-    }
     } else {
         // ------------------------------------------------------------------------------------------ softmax warps
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-        const int qb = (warp - 4) >> 2;
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        const uint32_t s_addr = lane_base + TM_S + qb * TM_STRIDE;
-        const uint32_t o_addr = lane_base + TM_O + qb * TM_STRIDE;
-        uint8_t* prow = sP + qb * C::P_BYTES + row * 128;
-        const uint32_t prow_u32 = smem_u32(prow);
+        const uint32_t o_addr = lane_base + TM_O;
+        const uint32_t prow_u32 = smem_u32(sP) + row * 128;
+        const uint32_t sw = static_cast<uint32_t>(row) & 7u;
         const bool f16 = p.f16 != 0;
-        uint32_t n = 0;  // key blocks processed by this query block (global count)
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-            const int qp = item % p.nqp;
-            const int h = (item / p.nqp) % p.H;
-            const int b = item / (p.nqp * p.H);
-            if ((qp * 2 + qb) * BLK >= p.S) continue;  // no such query block (loader and MMA warp skip it too)
-            const int tok = (qp * 2 + qb) * BLK + row;
-            // warps whose 32 rows all lie past the last token keep the barrier protocol but skip the arithmetic
-            const bool warp_live = (qp * 2 + qb) * BLK + quarter * 32 < p.S;
+        const float sc = p.scale_log2;
+        int t = 0;  // key blocks processed by this CTA
+        for (int it = 0; it < n_local; ++it) {
+            const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+            const int qb = item % p.nq;
+            const int h = (item / p.nq) % p.H;
+            const int b = item / (p.nq * p.H);
+            const int tok = qb * QB + row;
             float m = 0.f, l = 0.f;
-            for (int j = 0; j < J; ++j, ++n) {
-                const int valid = p.S - j * BLK;
-                const int nch = valid >= BLK ? 4 : (valid + 31) >> 5;  // 32-key chunks of this block
-                mbar_wait(&s_full[qb], n & 1);
+            for (int j = 0; j < J; ++j, ++t) {
+                const int sb = t & 1;
+                const int valid = p.S - j * KB;
+                const int nch = valid >= KB ? 4 : (valid + 15) >> 4;  // 16-key chunks of this block
+                mbar_wait(&s_full[sb], (t >> 1) & 1);
                 tc_fence_after();
-                uint32_t v[BLK];
-                if (warp_live) {
+                uint32_t v[KB];
+                const uint32_t s_addr = lane_base + TM_S + sb * KB;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (c < nch) tmem_ld_32x32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
-                    tmem_ld_wait();
-                }
+                for (int c = 0; c < 4; ++c)
+                    if (c < nch) tmem_ld_32x16(s_addr + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c * 16]));
+                tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[qb]);
+                if (lane == 0) mbar_arrive(&s_empty[sb]);
+                if (valid < nch * 16) {
+#pragma unroll
+                    for (int i = 0; i < KB; ++i)
+                        if (i >= valid) v[i] = 0xFF800000u;  // -inf: key past the end of the image
+                }
+                // independent max chains (one per 16-key chunk) instead of one 64-long dependent chain
+                float mxc[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    mxc[c] = __uint_as_float(v[0]);
+                    if (c < nch) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) mxc[c] = fmaxf(mxc[c], __uint_as_float(v[c * 16 + i]));
+                    }
+                }
+                const float tmax = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])) * sc;
                 float factor = 1.f;
                 bool need = false;
-                if (warp_live && !(p.dbg & 8)) {
-                    if (valid < nch * 32) {
-#pragma unroll
-                        for (int i = 0; i < BLK; ++i)
-                            if (i >= valid) v[i] = 0xFF800000u;  // -inf: key past the end of the image
-                    }
-                    // four independent max chains (one per 32-key chunk) instead of one 128-long dependent chain
-                    float mxc[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        mxc[c] = __uint_as_float(v[0]);
-                        if (c < nch) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) mxc[c] = fmaxf(mxc[c], __uint_as_float(v[c * 32 + i]));
-                        }
-                    }
-                    const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
-                    const float tmax = mx * p.scale_log2;
-                    if (j == 0) {
-                        m = tmax;
-                    } else if (tmax > m + 8.f) {
-                        factor = ex2_approx(m - tmax);
-                        m = tmax;
-                        need = true;
-                    }
+                if (j == 0) {
+                    m = tmax;
+                } else if (tmax > m + 8.f) {
+                    factor = ex2_approx(m - tmax);
+                    m = tmax;
+                    need = true;
                 }
-                if (j > 0) {
-                    // P·V of the previous block has finished: P (smem) and O (TMEM) may be touched again
-                    mbar_wait(&pv_done[qb], (n - 1) & 1);
-                    if (__any_sync(0xffffffffu, need)) {
-                        tc_fence_after();
+                if (j > 0 && __any_sync(0xffffffffu, need)) {
+                    // P·V of the previous block must have landed before O is rescaled
+                    mbar_wait(&p_empty[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                    tc_fence_after();
 #pragma unroll 1
-                        for (int c = 0; c < C::DHP / 16; ++c) {
-                            uint32_t o[16];
-                            tmem_ld_32x16(o_addr + c * 16, o);
-                            tmem_ld_wait();
+                    for (int c = 0; c < C::DHP / 16; ++c) {
+                        uint32_t o[16];
+                        tmem_ld_32x16(o_addr + c * 16, o);
+                        tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-                            tmem_st_32x16(o_addr + c * 16, o);
-                        }
-                        tmem_st_wait();
-                        l *= factor;
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                        tmem_st_32x16(o_addr + c * 16, o);
                     }
+                    tmem_st_wait();
+                    l *= factor;
                 }
-                if (warp_live && !(p.dbg & 1)) {
+                // this P tile was last read by P·V two blocks ago
+                mbar_wait(&p_empty[sb], ((t >> 1) & 1) ^ 1);
+                if (!(p.dbg & 1)) {
                     float sum[4] = {0.f, 0.f, 0.f, 0.f};
-                    const float neg_m = -m, sc = p.scale_log2;
+                    const float neg_m = -m;
+                    const uint32_t pdst = prow_u32 + sb * C::P_BYTES;
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {  // 16 chunks of 8 keys = 16 bytes of P
-                        if ((c >> 2) < nch) {
-                            // in place, 8 independent FFMA then 8 independent MUFU.EX2 (no shared temporary: the SFU
-                            // pipe is the bound of this kernel, the chain FFMA -> EX2 -> FFMA must not serialise)
+                    for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys = 16 bytes of P
+                        if ((c >> 1) < nch) {
+                            // in place, 8 independent FFMA then 8 independent MUFU.EX2 (the SFU pipe is the bound of this
+                            // kernel: the chain FFMA -> EX2 -> FADD must not serialise)
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
                                 v[c * 8 + i] = __float_as_uint(fmaf(__uint_as_float(v[c * 8 + i]), sc, neg_m));
@@ -352,11 +366,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
                                 const float e0 = __uint_as_float(v[c * 8 + 2 * i]), e1 = __uint_as_float(v[c * 8 + 2 * i + 1]);
                                 w[i] = f16 ? pack_f16x2(e0, e1) : pack_bf16x2(e0, e1);
                             }
-                            // K-major SWIZZLE_128B A tile: key group (c >> 3) is a [128 x 128 B] slab, 16-byte chunk
-                            // (c & 7) of this row sits at chunk index (c & 7) ^ (row & 7)
-                            const uint32_t dst = prow_u32 + (c >> 3) * 16384 + ((((c & 7) ^ (row & 7))) << 4);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[0]), "r"(w[1]),
-                                         "r"(w[2]), "r"(w[3])
+                            // K-major SWIZZLE_128B A tile [128 rows x 128 B]: 16-byte chunk c of this row at c ^ (row & 7)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pdst + ((static_cast<uint32_t>(c) ^ sw) << 4)),
+                                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
                                          : "memory");
                         }
                     }
@@ -365,22 +377,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
                 fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[qb]);
+                if (lane == 0) mbar_arrive(&p_full[sb]);
             }
             // ---- epilogue: O / l -> 16-bit -> ctx[b, tok, h*dh : (h+1)*dh]
-            mbar_wait(&pv_done[qb], (n - 1) & 1);
+            mbar_wait(o_full, it & 1);
             tc_fence_after();
-            const float inv = 1.f / l;
-            uint16_t* orow = static_cast<uint16_t*>(p.out) + (static_cast<size_t>(b) * p.S + tok) * p.D + h * DH;
-            const bool tok_ok = tok < p.S;
             uint32_t o[C::DHP];
 #pragma unroll
             for (int c = 0; c < C::DHP / 16; ++c) tmem_ld_32x16(o_addr + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&o[c * 16]));
             tmem_ld_wait();
             tc_fence_before();  // O is in registers: hand the accumulator back to the MMA warp
             __syncwarp();
-            if (lane == 0) mbar_arrive(&o_empty[qb]);
-            if (tok_ok) {
+            if (lane == 0) mbar_arrive(o_empty);
+            if (tok < p.S) {
+                const float inv = 1.f / l;
+                uint16_t* orow = static_cast<uint16_t*>(p.out) + (static_cast<size_t>(b) * p.S + tok) * p.D + h * DH;
 #pragma unroll
                 for (int c = 0; c < C::DHP / 8; ++c) {
                     if (c * 8 < DH) {
@@ -401,7 +412,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_main, const __grid_c
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, 256);
     }
 }
 
@@ -420,15 +431,15 @@ struct MapKeyHash {
         return h;
     }
 };
-struct MapPair {
-    CUtensorMap main, tail;
+struct MapSet {
+    CUtensorMap q, qt, kv, kvt;
 };
 
 template <int DH>
-int get_maps(const void* qkv, bool f16, int B, int S, int H, MapPair* out) {
+int get_maps(const void* qkv, bool f16, int B, int S, int H, MapSet* out) {
     using C = TcCfg<DH>;
     static std::mutex mu;
-    static std::unordered_map<MapKey, MapPair, MapKeyHash> cache;
+    static std::unordered_map<MapKey, MapSet, MapKeyHash> cache;
     MapKey key{qkv, B, S, H, DH, f16 ? 1 : 0};
     {
         std::lock_guard<std::mutex> lk(mu);
@@ -443,31 +454,37 @@ int get_maps(const void* qkv, bool f16, int B, int S, int H, MapPair* out) {
     const uint64_t dims[5] = {static_cast<uint64_t>(DH), static_cast<uint64_t>(H), 3, static_cast<uint64_t>(S),
                               static_cast<uint64_t>(B)};
     const uint64_t strides[4] = {static_cast<uint64_t>(DH) * 2, D * 2, 3 * D * 2, static_cast<uint64_t>(S) * 3 * D * 2};
-    const uint32_t box_main[5] = {64, 1, 1, BLK, 1};
-    MapPair mp;
-    int rc = encode_tensor_map(&mp.main, f16, 5, qkv, dims, strides, box_main, 128);
+    const uint32_t box_q[5] = {64, 1, 1, QB, 1}, box_kv[5] = {64, 1, 1, KB, 1};
+    MapSet ms;
+    int rc = encode_tensor_map(&ms.q, f16, 5, qkv, dims, strides, box_q, 128);
+    if (rc != VLMFW_OK) return rc;
+    rc = encode_tensor_map(&ms.kv, f16, 5, qkv, dims, strides, box_kv, 128);
     if (rc != VLMFW_OK) return rc;
     if (C::TAIL) {
-        const uint32_t box_tail[5] = {static_cast<uint32_t>(C::TAIL), 1, 1, BLK, 1};
-        rc = encode_tensor_map(&mp.tail, f16, 5, qkv, dims, strides, box_tail, C::TAIL_ROW);
+        const uint32_t box_qt[5] = {static_cast<uint32_t>(C::TAIL), 1, 1, QB, 1};
+        const uint32_t box_kvt[5] = {static_cast<uint32_t>(C::TAIL), 1, 1, KB, 1};
+        rc = encode_tensor_map(&ms.qt, f16, 5, qkv, dims, strides, box_qt, C::TAIL_ROW);
+        if (rc != VLMFW_OK) return rc;
+        rc = encode_tensor_map(&ms.kvt, f16, 5, qkv, dims, strides, box_kvt, C::TAIL_ROW);
         if (rc != VLMFW_OK) return rc;
     } else {
-        mp.tail = mp.main;
+        ms.qt = ms.q;
+        ms.kvt = ms.kv;
     }
     {
         std::lock_guard<std::mutex> lk(mu);
         if (cache.size() > 1024) cache.clear();
-        cache.emplace(key, mp);
+        cache.emplace(key, ms);
     }
-    *out = mp;
+    *out = ms;
     return VLMFW_OK;
 }
 
 template <int DH>
 int launch_tc(const void* qkv, bool f16, int batch, int tokens, int heads, void* out, cudaStream_t stream) {
     using C = TcCfg<DH>;
-    MapPair mp;
-    int rc = get_maps<DH>(qkv, f16, batch, tokens, heads, &mp);
+    MapSet ms;
+    int rc = get_maps<DH>(qkv, f16, batch, tokens, heads, &ms);
     if (rc != VLMFW_OK) return rc;
     auto kern = attention_tc_kernel<DH>;
     static bool attr_set = false;
@@ -481,18 +498,18 @@ int launch_tc(const void* qkv, bool f16, int batch, int tokens, int heads, void*
     p.H = heads;
     p.B = batch;
     p.D = heads * DH;
-    const int nq = (tokens + BLK - 1) / BLK;
-    p.nqp = (nq + 1) / 2;
-    p.J = nq;
-    p.num_items = batch * heads * p.nqp;
+    p.nq = (tokens + QB - 1) / QB;
+    p.J = (tokens + KB - 1) / KB;
+    p.num_items = batch * heads * p.nq;
     p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
     p.f16 = f16 ? 1 : 0;
     {
         const char* e = getenv("VLMFW_ATTN_DBG");
         p.dbg = e ? atoi(e) : 0;
     }
-    const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
-    kern<<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(mp.main, mp.tail, p);
+    const int slots = 2 * num_sms();
+    const int grid = p.num_items < slots ? p.num_items : slots;
+    kern<<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(ms.q, ms.qt, ms.kv, ms.kvt, p);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
