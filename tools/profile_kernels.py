@@ -1,5 +1,5 @@
 """One launch sequence of the hot kernels at the headline shapes (SigLIP-So400m, batch 256 -> M = 65536), for
-`ncu --set full -k regex:'gemm_bf16_tn|attention_kernel|layernorm_kernel|pool_ln_mean|im2col'`. Each kernel runs twice
+`ncu --set full -k regex:'gemm_bf16_tn|attention_tc|row_stats_cast|pool_ln_mean|im2col'`. Each kernel runs twice
 (first = warm-up: tensor maps, func attributes); profile the second with --launch-skip or read both."""
 import math
 import os
@@ -26,14 +26,18 @@ w1, b1 = rn(I, D, sc=1 / math.sqrt(D)).to(DT), rn(I, sc=0.1)
 w2, b2 = rn(D, I, sc=1 / math.sqrt(I)).to(DT), rn(D, sc=0.1)
 pix = torch.randint(0, 256, (B, 224, 224, 3), device=dev, dtype=torch.uint8, generator=g)
 
-for it in range(2):
+w1f, b1c = ops.ln_fold_weight(rn(I, D, sc=1 / math.sqrt(D)), gamma, beta, b1, dtype=DT)
+wqf, bqc = ops.ln_fold_weight(rn(3 * D, D, sc=1 / math.sqrt(D)), gamma, beta, bqkv, dtype=DT)
+parts = ops.gemm_stats_parts(D)
+
+for it in range(2):  # the tower's launch sequence for one layer (tower.cu), at the headline shapes
     a = ops.im2col(pix, 224, 14, 592, spec.pix_mean, spec.pix_std, dtype=DT)
-    xn = ops.layernorm(h, gamma, beta, 1e-6, dtype=DT)
-    qkv = ops.gemm_tn(xn, wqkv, bqkv)
+    xn, stats = ops.row_stats_cast(h, dtype=DT, parts=parts)
+    qkv = ops.gemm_tn_ln(xn, wqf, bqc, stats, D, 1e-6)
     ctx = ops.attention(qkv, B, spec.tokens, spec.heads, spec.head_dim)
-    ops.gemm_tn(ctx, wo, bo, resid=h, out=h)
-    mid = ops.gemm_tn(xn, w1, b1, act=spec.act)
-    ops.gemm_tn(mid, w2, b2, resid=h, out=h)
+    xn, stats = ops.gemm_tn_resid_stats(ctx, wo, bo, h)
+    mid = ops.gemm_tn_ln(xn, w1f, b1c, stats, D, 1e-6, act=spec.act)
+    xn, stats = ops.gemm_tn_resid_stats(mid, w2, b2, h)
     pooled = ops.pool(h.view(B, spec.tokens, D), specs.POOL_LN_MEAN, gamma, beta, 1e-6)
     if os.environ.get("VLMFW_PROFILE_CUBLAS") == "1":  # the library GEMM on the fc1 shape, for a side-by-side ncu read
         torch.matmul(xn, w1.t())
