@@ -51,7 +51,7 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* smem_tile, const __nv_b
 template <int DHP, bool F16>
 __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                 __nv_bfloat16* __restrict__ out, int tokens,
-                                                                int heads, int dh, float scale_log2) {
+                                                                int heads, int dh, float scale_log2, int q_begin) {
     using C = AttCfg<DHP>;
     constexpr int KSTEPS = DHP / 16;  // k-steps of Q K^T
     constexpr int NT_O = DHP / 8;     // n-tiles of the output accumulator
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __nv_bfloa
     __nv_bfloat16* sK = sQ + C::TILE_ELEMS;      // [2][64][PITCH]
     __nv_bfloat16* sV = sK + 2 * C::TILE_ELEMS;  // [2][64][PITCH]
 
-    const int q0 = blockIdx.x * BQ;
+    const int q0 = q_begin + blockIdx.x * BQ;
     const int head = blockIdx.y;
     const int img = blockIdx.z;
     const int dmodel = heads * dh;
@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __nv_bfloa
 }
 
 template <int DHP, bool F16>
-int launch_att(const void* qkv, int batch, int tokens, int heads, int dh, void* out, cudaStream_t stream) {
+int launch_att(const void* qkv, int batch, int tokens, int heads, int dh, void* out, cudaStream_t stream,
+               int q_begin = 0) {
     using C = AttCfg<DHP>;
     auto kern = attention_kernel<DHP, F16>;
     static bool attr_set = false;
@@ -230,10 +231,11 @@ int launch_att(const void* qkv, int batch, int tokens, int heads, int dh, void* 
         VLMFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    dim3 grid((tokens + BQ - 1) / BQ, heads, batch);
+    dim3 grid((tokens - q_begin + BQ - 1) / BQ, heads, batch);
     const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
     kern<<<grid, ATT_THREADS, C::SMEM_BYTES, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
-                                                       static_cast<__nv_bfloat16*>(out), tokens, heads, dh, scale_log2);
+                                                       static_cast<__nv_bfloat16*>(out), tokens, heads, dh, scale_log2,
+                                                       q_begin);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
@@ -254,18 +256,25 @@ int launch_attention(const void* qkv, bool f16, int batch, int tokens, int heads
         const char* e = getenv("VLMFW_ATTN_LEGACY");
         return e != nullptr && e[0] == '1';
     }();
+    // The tcgen05 kernel can be limited to the first q_tail query rows with the generic kernel taking the rest (disjoint
+    // output rows, same stream). Measured on EVA (257 = 2 x 128 + the class token) the generic kernel's 64-query tile for
+    // that one row costs more than the tcgen05 kernel's third, mostly idle, work item (0.445 vs 0.412 ms at B = 255), so
+    // the split stays off and the tcgen05 kernel skips the arithmetic of softmax warps whose rows lie past the sequence.
+    const int q_tail = tokens;
     if (!legacy) {
-        rc = launch_attention_tc(qkv, f16, batch, tokens, heads, head_dim, out, stream);
-        if (rc <= 0) return rc;
+        rc = launch_attention_tc(qkv, f16, batch, tokens, heads, head_dim, out, q_tail, stream);
+        if (rc < 0) return rc;
+        if (rc == 0 && q_tail == tokens) return rc;
     }
+    const int q_begin = (!legacy && rc == 0) ? q_tail : 0;
     if (f16) {
-        if (head_dim <= 64) return launch_att<64, true>(qkv, batch, tokens, heads, head_dim, out, stream);
-        if (head_dim <= 80) return launch_att<80, true>(qkv, batch, tokens, heads, head_dim, out, stream);
-        return launch_att<96, true>(qkv, batch, tokens, heads, head_dim, out, stream);
+        if (head_dim <= 64) return launch_att<64, true>(qkv, batch, tokens, heads, head_dim, out, stream, q_begin);
+        if (head_dim <= 80) return launch_att<80, true>(qkv, batch, tokens, heads, head_dim, out, stream, q_begin);
+        return launch_att<96, true>(qkv, batch, tokens, heads, head_dim, out, stream, q_begin);
     }
-    if (head_dim <= 64) return launch_att<64, false>(qkv, batch, tokens, heads, head_dim, out, stream);
-    if (head_dim <= 80) return launch_att<80, false>(qkv, batch, tokens, heads, head_dim, out, stream);
-    return launch_att<96, false>(qkv, batch, tokens, heads, head_dim, out, stream);
+    if (head_dim <= 64) return launch_att<64, false>(qkv, batch, tokens, heads, head_dim, out, stream, q_begin);
+    if (head_dim <= 80) return launch_att<80, false>(qkv, batch, tokens, heads, head_dim, out, stream, q_begin);
+    return launch_att<96, false>(qkv, batch, tokens, heads, head_dim, out, stream, q_begin);
 }
 
 }  // namespace vlmfw

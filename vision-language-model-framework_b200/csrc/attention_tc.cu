@@ -34,7 +34,15 @@ namespace {
 constexpr int TC_THREADS = 192;  // loader warp, MMA warp, 4 softmax warps (TMEM lane quarter = warp % 4)
 constexpr int QB = 128;          // query rows per item (= TMEM lanes)
 constexpr int KB = 64;           // keys per block
-constexpr int NKV = 2;           // K / V ring depth
+#ifndef VLMFW_ATT_NKV
+#define VLMFW_ATT_NKV 2
+#endif
+#ifndef VLMFW_ATT_NP
+#define VLMFW_ATT_NP 2
+#endif
+constexpr int NKV_WANT = VLMFW_ATT_NKV;  // K / V ring depth asked for (<= 4); each head dim takes what fits
+constexpr int NP = VLMFW_ATT_NP;         // P tiles (1 or 2)
+constexpr int SMEM_PER_CTA = 233472 / 2 - 1024;  // two CTAs per SM, 1 KB reserved per CTA
 
 template <int DH>
 struct TcCfg {
@@ -48,8 +56,11 @@ struct TcCfg {
     static constexpr int KV_BYTES = KV_MAIN + KB * TAIL_ROW;
     static constexpr int P_BYTES = QB * KB * 2;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = Q_BYTES + 2 * NKV * KV_BYTES + 2 * P_BYTES + BAR_BYTES + 1024;
-    static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two CTAs must fit one SM's shared memory");
+    static constexpr int FIXED = Q_BYTES + NP * P_BYTES + BAR_BYTES + 1024;
+    static constexpr int NKV_FIT = (SMEM_PER_CTA - FIXED) / (2 * KV_BYTES);
+    static constexpr int NKV = NKV_FIT < NKV_WANT ? NKV_FIT : NKV_WANT;
+    static_assert(NKV >= 2, "K / V rings need two stages");
+    static constexpr int SMEM_BYTES = FIXED + 2 * NKV * KV_BYTES;
 };
 
 struct TcParams {
@@ -80,7 +91,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
-template <int DH>
+template <int DH, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qt,
                     const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_kvt,
@@ -89,23 +100,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                         // [Q_BYTES]
-    uint8_t* sK = sQ + C::Q_BYTES;              // [NKV][KV_BYTES]
-    uint8_t* sV = sK + NKV * C::KV_BYTES;       // [NKV][KV_BYTES]
-    uint8_t* sP = sV + NKV * C::KV_BYTES;       // [2][P_BYTES]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * C::P_BYTES);
+    uint8_t* sK = sQ + C::Q_BYTES;              // [C::NKV][KV_BYTES]
+    uint8_t* sV = sK + C::NKV * C::KV_BYTES;       // [C::NKV][KV_BYTES]
+    uint8_t* sP = sV + C::NKV * C::KV_BYTES;       // [NP][P_BYTES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NP * C::P_BYTES);
     uint64_t* q_full = bars + 0;
     uint64_t* q_empty = bars + 1;
-    uint64_t* k_full = bars + 2;    // [NKV]
-    uint64_t* k_empty = bars + 4;   // [NKV]
-    uint64_t* v_full = bars + 6;    // [NKV]
-    uint64_t* v_empty = bars + 8;   // [NKV]
-    uint64_t* s_full = bars + 10;   // [2] score buffers
-    uint64_t* s_empty = bars + 12;  // [2]
-    uint64_t* p_full = bars + 14;   // [2] probability tiles
-    uint64_t* p_empty = bars + 16;  // [2] (= P·V of that block complete: P free, O updated)
-    uint64_t* o_full = bars + 18;
-    uint64_t* o_empty = bars + 19;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* o_full = bars + 2;
+    uint64_t* o_empty = bars + 3;
+    uint64_t* s_full = bars + 4;    // [2] score buffers
+    uint64_t* s_empty = bars + 6;   // [2]
+    uint64_t* p_full = bars + 8;    // [2] probability tiles
+    uint64_t* p_empty = bars + 10;  // [2] (= P·V of that block complete: P free, O updated)
+    uint64_t* k_full = bars + 12;   // [4]
+    uint64_t* k_empty = bars + 16;  // [4]
+    uint64_t* v_full = bars + 20;   // [4]
+    uint64_t* v_empty = bars + 24;  // [4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -119,11 +130,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         mbar_init(q_full, 1);
         mbar_init(q_empty, 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
             mbar_init(&k_full[i], 1);
             mbar_init(&k_empty[i], 1);
             mbar_init(&v_full[i], 1);
             mbar_init(&v_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
             mbar_init(&s_empty[i], 4);
             mbar_init(&p_full[i], 4);
@@ -172,8 +185,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         tma_load_5d(sQ, &map_q, q_full, 0, h, 0, qb * QB, b);
                         if (C::TAIL) tma_load_5d(sQ + C::Q_MAIN, &map_qt, q_full, 64, h, 0, qb * QB, b);
                     }
-                    const int st = s % NKV;
-                    mbar_wait(&k_empty[st], ((s / NKV) & 1) ^ 1);
+                    const int st = s % C::NKV;
+                    mbar_wait(&k_empty[st], ((s / C::NKV) & 1) ^ 1);
                     mbar_arrive_expect_tx(&k_full[st], C::KV_BYTES);
                     tma_load_5d(sK + st * C::KV_BYTES, &map_kv, &k_full[st], 0, h, 1, j * KB, b);
                     if (C::TAIL) tma_load_5d(sK + st * C::KV_BYTES + C::KV_MAIN, &map_kvt, &k_full[st], 64, h, 1, j * KB, b);
@@ -181,8 +194,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 if (s >= 1) {
                     const int sv = s - 1;
                     coords(sv, b, h, j, qb);
-                    const int st = sv % NKV;
-                    mbar_wait(&v_empty[st], ((sv / NKV) & 1) ^ 1);
+                    const int st = sv % C::NKV;
+                    mbar_wait(&v_empty[st], ((sv / C::NKV) & 1) ^ 1);
                     mbar_arrive_expect_tx(&v_full[st], C::KV_BYTES);
                     tma_load_5d(sV + st * C::KV_BYTES, &map_kv, &v_full[st], 0, h, 2, j * KB, b);
                     if (C::TAIL) tma_load_5d(sV + st * C::KV_BYTES + C::KV_MAIN, &map_kvt, &v_full[st], 64, h, 2, j * KB, b);
@@ -192,7 +205,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     } else if (warp == 1) {
         // ------------------------------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            const bool f16 = p.f16 != 0;
+            constexpr bool f16 = F16;
             const uint32_t idesc_pv = umma_idesc_16_bmn(QB, 64, f16);
             const uint32_t idesc_pvt = umma_idesc_16_bmn(QB, C::TAIL ? C::TAIL : 16, f16);
             const uint32_t q_u32 = smem_u32(sQ), k_u32 = smem_u32(sK), v_u32 = smem_u32(sV), p_u32 = smem_u32(sP);
@@ -205,9 +218,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             // The key blocks of all of this CTA's items form one stream t = 0 .. T-1 (item t / J, block t % J)
             const int T = n_local * J;
             auto issue_s = [&](int t) {
-                const int k = t / J, j = t - k * J, st = t % NKV, sb = t & 1;
+                const int k = t / J, j = t - k * J, st = t % C::NKV, sb = t & 1;
                 if (j == 0) mbar_wait(q_full, k & 1);
-                mbar_wait(&k_full[st], (t / NKV) & 1);
+                mbar_wait(&k_full[st], (t / C::NKV) & 1);
                 mbar_wait(&s_empty[sb], ((t >> 1) & 1) ^ 1);
                 tc_fence_after();
                 if (!(p.dbg & 4)) {
@@ -229,9 +242,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 if (j == J - 1) umma_commit(q_empty);
             };
             auto issue_pv = [&](int t) {
-                const int k = t / J, j = t - k * J, st = t % NKV, pb = t & 1;
-                mbar_wait(&v_full[st], (t / NKV) & 1);
-                mbar_wait(&p_full[pb], (t >> 1) & 1);
+                const int k = t / J, j = t - k * J, st = t % C::NKV, pb = t % NP;
+                mbar_wait(&v_full[st], (t / C::NKV) & 1);
+                mbar_wait(&p_full[pb], (t / NP) & 1);
                 if (j == 0) mbar_wait(o_empty, (k & 1) ^ 1);
                 tc_fence_after();
                 if (!(p.dbg & 2)) {
@@ -275,7 +288,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const uint32_t o_addr = lane_base + TM_O;
         const uint32_t prow_u32 = smem_u32(sP) + row * 128;
         const uint32_t sw = static_cast<uint32_t>(row) & 7u;
-        const bool f16 = p.f16 != 0;
         const float sc = p.scale_log2;
         int t = 0;  // key blocks processed by this CTA
         for (int it = 0; it < n_local; ++it) {
@@ -284,6 +296,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             const int h = (item / p.nq) % p.H;
             const int b = item / (p.nq * p.H);
             const int tok = qb * QB + row;
+            // warps whose 32 rows all lie past the last token (ragged last query block: EVA 257, CLIP 577) keep the
+            // barrier protocol but skip the TMEM reads and the arithmetic
+            const bool warp_live = qb * QB + quarter * 32 < p.S;
             float m = 0.f, l = 0.f;
             for (int j = 0; j < J; ++j, ++t) {
                 const int sb = t & 1;
@@ -293,27 +308,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 tc_fence_after();
                 uint32_t v[KB];
                 const uint32_t s_addr = lane_base + TM_S + sb * KB;
+                if (warp_live) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c < nch) tmem_ld_32x16(s_addr + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c * 16]));
-                tmem_ld_wait();
+                    for (int c = 0; c < 4; ++c)
+                        if (c < nch) tmem_ld_32x16(s_addr + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c * 16]));
+                    tmem_ld_wait();
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_empty[sb]);
+                if (!warp_live) {  // nothing to compute: release the P tile in step with the other warps
+                    const int pbd = t % NP;
+                    mbar_wait(&p_empty[pbd], ((t / NP) & 1) ^ 1);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_full[pbd]);
+                    continue;
+                }
                 if (valid < nch * 16) {
 #pragma unroll
                     for (int i = 0; i < KB; ++i)
                         if (i >= valid) v[i] = 0xFF800000u;  // -inf: key past the end of the image
                 }
-                // independent max chains (one per 16-key chunk) instead of one 64-long dependent chain
+                // independent max chains (one per 16-key chunk) instead of one 64-long dependent chain; a ragged last
+                // block has -inf in every column past `valid` (set above, also for the chunks that were not loaded)
+                const bool full = nch == 4;
+                if (!full) {
+#pragma unroll
+                    for (int c = 1; c < 4; ++c)
+                        if (c >= nch) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[c * 16 + i] = 0xFF800000u;
+                        }
+                }
                 float mxc[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    mxc[c] = __uint_as_float(v[0]);
-                    if (c < nch) {
+                    mxc[c] = __uint_as_float(v[c * 16]);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) mxc[c] = fmaxf(mxc[c], __uint_as_float(v[c * 16 + i]));
-                    }
+                    for (int i = 1; i < 16; ++i) mxc[c] = fmaxf(mxc[c], __uint_as_float(v[c * 16 + i]));
                 }
                 const float tmax = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3])) * sc;
                 float factor = 1.f;
@@ -327,7 +360,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 }
                 if (j > 0 && __any_sync(0xffffffffu, need)) {
                     // P·V of the previous block must have landed before O is rescaled
-                    mbar_wait(&p_empty[(t - 1) & 1], ((t - 1) >> 1) & 1);
+                    mbar_wait(&p_empty[(t - 1) % NP], ((t - 1) / NP) & 1);
                     tc_fence_after();
 #pragma unroll 1
                     for (int c = 0; c < C::DHP / 16; ++c) {
@@ -341,43 +374,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     tmem_st_wait();
                     l *= factor;
                 }
-                // this P tile was last read by P·V two blocks ago
-                mbar_wait(&p_empty[sb], ((t >> 1) & 1) ^ 1);
+                // this P tile was last read by P·V NP blocks ago
+                const int pb = t % NP;
+                mbar_wait(&p_empty[pb], ((t / NP) & 1) ^ 1);
                 if (!(p.dbg & 1)) {
                     float sum[4] = {0.f, 0.f, 0.f, 0.f};
                     const float neg_m = -m;
-                    const uint32_t pdst = prow_u32 + sb * C::P_BYTES;
+                    const uint32_t pdst = prow_u32 + pb * C::P_BYTES;
+                    // straight-line over the whole 64-key block: the columns of a ragged last block hold -inf (exp2 -> 0)
+                    // and its P chunks past kcols are written but never read by the narrower P·V
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys = 16 bytes of P
-                        if ((c >> 1) < nch) {
-                            // in place, 8 independent FFMA then 8 independent MUFU.EX2 (the SFU pipe is the bound of this
-                            // kernel: the chain FFMA -> EX2 -> FADD must not serialise)
+                        // in place, 8 independent FFMA then 8 independent MUFU.EX2 (the chain FFMA -> EX2 -> FADD must
+                        // not serialise)
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                v[c * 8 + i] = __float_as_uint(fmaf(__uint_as_float(v[c * 8 + i]), sc, neg_m));
+                        for (int i = 0; i < 8; ++i)
+                            v[c * 8 + i] = __float_as_uint(fmaf(__uint_as_float(v[c * 8 + i]), sc, neg_m));
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                v[c * 8 + i] = __float_as_uint(ex2_approx(__uint_as_float(v[c * 8 + i])));
+                        for (int i = 0; i < 8; ++i)
+                            v[c * 8 + i] = __float_as_uint(ex2_approx(__uint_as_float(v[c * 8 + i])));
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) sum[i & 3] += __uint_as_float(v[c * 8 + i]);
-                            uint32_t w[4];
+                        for (int i = 0; i < 8; ++i) sum[i & 3] += __uint_as_float(v[c * 8 + i]);
+                        uint32_t w[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float e0 = __uint_as_float(v[c * 8 + 2 * i]), e1 = __uint_as_float(v[c * 8 + 2 * i + 1]);
-                                w[i] = f16 ? pack_f16x2(e0, e1) : pack_bf16x2(e0, e1);
-                            }
-                            // K-major SWIZZLE_128B A tile [128 rows x 128 B]: 16-byte chunk c of this row at c ^ (row & 7)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pdst + ((static_cast<uint32_t>(c) ^ sw) << 4)),
-                                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                                         : "memory");
+                        for (int i = 0; i < 4; ++i) {
+                            const float e0 = __uint_as_float(v[c * 8 + 2 * i]), e1 = __uint_as_float(v[c * 8 + 2 * i + 1]);
+                            w[i] = pack_16x2<F16>(e0, e1);
                         }
+                        // K-major SWIZZLE_128B A tile [128 rows x 128 B]: 16-byte chunk c of this row at c ^ (row & 7)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pdst + ((static_cast<uint32_t>(c) ^ sw) << 4)),
+                                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                                     : "memory");
                     }
                     l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
                 }
                 fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[sb]);
+                if (lane == 0) mbar_arrive(&p_full[pb]);
             }
             // ---- epilogue: O / l -> 16-bit -> ctx[b, tok, h*dh : (h+1)*dh]
             mbar_wait(o_full, it & 1);
@@ -399,7 +433,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const float x0 = __uint_as_float(o[c * 8 + 2 * i]) * inv, x1 = __uint_as_float(o[c * 8 + 2 * i + 1]) * inv;
-                            w[i] = f16 ? pack_f16x2(x0, x1) : pack_bf16x2(x0, x1);
+                            w[i] = pack_16x2<F16>(x0, x1);
                         }
                         *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
@@ -480,13 +514,14 @@ int get_maps(const void* qkv, bool f16, int B, int S, int H, MapSet* out) {
     return VLMFW_OK;
 }
 
-template <int DH>
-int launch_tc(const void* qkv, bool f16, int batch, int tokens, int heads, void* out, cudaStream_t stream) {
+template <int DH, bool F16>
+int launch_tc(const void* qkv, int batch, int tokens, int heads, void* out, int q_rows, cudaStream_t stream) {
     using C = TcCfg<DH>;
+    constexpr bool f16 = F16;
     MapSet ms;
     int rc = get_maps<DH>(qkv, f16, batch, tokens, heads, &ms);
     if (rc != VLMFW_OK) return rc;
-    auto kern = attention_tc_kernel<DH>;
+    auto kern = attention_tc_kernel<DH, F16>;
     static bool attr_set = false;
     if (!attr_set) {
         VLMFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -498,7 +533,7 @@ int launch_tc(const void* qkv, bool f16, int batch, int tokens, int heads, void*
     p.H = heads;
     p.B = batch;
     p.D = heads * DH;
-    p.nq = (tokens + QB - 1) / QB;
+    p.nq = (q_rows + QB - 1) / QB;
     p.J = (tokens + KB - 1) / KB;
     p.num_items = batch * heads * p.nq;
     p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
@@ -519,16 +554,19 @@ int launch_tc(const void* qkv, bool f16, int batch, int tokens, int heads, void*
 // head_dim 64 / 72 / 88 (the three towers) run on tcgen05; returns 1 when the shape is not covered (caller falls back to
 // the generic mma.sync kernel of attention.cu, which takes any head_dim % 8 == 0 up to 96).
 int launch_attention_tc(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out,
-                        cudaStream_t stream) {
+                        int q_rows, cudaStream_t stream) {
     const size_t row_bytes = static_cast<size_t>(3) * heads * head_dim * 2;
     if ((reinterpret_cast<uintptr_t>(qkv) & 15) != 0 || row_bytes % 16 != 0) return 1;
     switch (head_dim) {
         case 64:
-            return launch_tc<64>(qkv, f16, batch, tokens, heads, out, stream);
+            return f16 ? launch_tc<64, true>(qkv, batch, tokens, heads, out, q_rows, stream)
+                       : launch_tc<64, false>(qkv, batch, tokens, heads, out, q_rows, stream);
         case 72:
-            return launch_tc<72>(qkv, f16, batch, tokens, heads, out, stream);
+            return f16 ? launch_tc<72, true>(qkv, batch, tokens, heads, out, q_rows, stream)
+                       : launch_tc<72, false>(qkv, batch, tokens, heads, out, q_rows, stream);
         case 88:
-            return launch_tc<88>(qkv, f16, batch, tokens, heads, out, stream);
+            return f16 ? launch_tc<88, true>(qkv, batch, tokens, heads, out, q_rows, stream)
+                       : launch_tc<88, false>(qkv, batch, tokens, heads, out, q_rows, stream);
         default:
             return 1;
     }
