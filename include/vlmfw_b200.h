@@ -146,6 +146,33 @@ int64_t vlmfw_tower_last_launches(const vlmfw_tower* t);
  * host_pixels: VLMFW_PIX_U8_NHWC bytes; host_pooled: [B, D] floats. Buffers are owned by the handle. */
 int vlmfw_tower_forward_host(vlmfw_tower* t, const uint8_t* host_pixels, int32_t batch, float* host_pooled);
 
+/* ------------------------------------------------------------------ image ingest
+ * Replaces the CPU image-processor call in front of every tower forward (reference models/paligemma.py:108,
+ * models/llava.py:109, models/blip2.py:91 -> transformers TorchvisionBackend.resize / center_crop on uint8 tensors):
+ * raw RGB images of any size -> uint8 [B, S, S, 3], bit-exact with that processor's resized image (bicubic, antialias,
+ * ATen's fixed-point separable kernel). The rescale + normalize that follows is fused into the tower's patch gather
+ * (VLMFW_PIX_U8_NHWC). */
+enum {
+    VLMFW_RESIZE_SQUARE = 0,       /* resize to S x S ignoring aspect (SigLIP, BLIP image processors)              */
+    VLMFW_RESIZE_SHORTEST_CROP = 1 /* shortest edge -> S (long = int(S * long / short)), centre crop S x S (CLIP) */
+};
+typedef struct vlmfw_preproc vlmfw_preproc;
+int vlmfw_preproc_create(int32_t mode, int32_t out_size, vlmfw_preproc** out);
+void vlmfw_preproc_destroy(vlmfw_preproc* p);
+/* device workspace a batch with these image sizes needs (descriptor + weight tables + horizontal-pass rows) */
+size_t vlmfw_preproc_workspace_bytes(vlmfw_preproc* p, const int32_t* heights_host, const int32_t* widths_host,
+                                     int32_t batch);
+/* packed: DEVICE bytes (16-byte aligned), image i = RGB HWC at packed + offsets_host[i], heights/widths/offsets HOST
+ * arrays of `batch` entries. out: DEVICE uint8 [batch, S, S, 3]. Two launches per call, asynchronous on `stream`. */
+int vlmfw_preproc_run(vlmfw_preproc* p, const uint8_t* packed, int64_t packed_bytes, const int64_t* offsets_host,
+                      const int32_t* heights_host, const int32_t* widths_host, int32_t batch, uint8_t* out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int64_t vlmfw_preproc_last_launches(const vlmfw_preproc* p);
+/* HOST-only (no device needed): tap windows and int16 weights of output positions [offset, offset + count) of the
+ * in_size -> out_full antialiased bicubic resize; weights [count, weights_ld], *taps <= weights_ld. */
+int vlmfw_resize_weights(int32_t in_size, int32_t out_full, int32_t offset, int32_t count, int32_t* xmin,
+                         int32_t* xsize, int16_t* weights, int32_t weights_ld, int32_t* taps, int32_t* precision);
+
 /* ------------------------------------------------------------------ probe */
 /* pooled [B,D] -> packed logits [B, sum C] (+ per-head argmax [B, n_heads], first-max tie rule of torch.argmax).
  * `heads` is a HOST array of n_heads descriptors. */

@@ -74,23 +74,32 @@ def test_plugin_matches_reference_golden(cuda_device, name):
         assert torch.nn.functional.cosine_similarity(cls, torch.from_numpy(g["features_cls"])).min() >= COS_MIN
 
 
-def test_non_native_size_goes_through_hf_processor(cuda_device):
-    """Images that are not already 224x224 take the unchanged HF processor (CPU bicubic resize) and the fp32 NCHW
-    ingest path; result must agree with the oracle run on the same processor output."""
+@pytest.mark.parametrize("name", ["siglip_tiny", "clip_tiny", "eva_tiny"])
+def test_non_native_sizes_resized_on_gpu_equal_hf_processor_path(cuda_device, name):
+    """Images that are not already S x S: the default path resizes them on the GPU (ingest.ImageIngest), the opt-out
+    keeps the unchanged HF processor (CPU resize, fp32 NCHW ingest). The GPU resize is bit-exact with the processor's
+    uint8 resize, so both must agree with the oracle on the processor's pixel_values, and with each other almost to the
+    bit (only the fused rescale + normalize differs in the last ulp)."""
     from PIL import Image
 
     from oracle import hf_ref
 
-    spec = specs.SIGLIP_TINY
+    spec = specs.SPECS[name]
     sd = weights.seeded_hf_state_dict(spec, 2)
     proc = hf_ref.ProcessorShim(hf_ref.build_hf_processor(spec))
     bb = backbone_from_spec(spec, sd, device="cuda", processor=proc)
-    big = weights.seeded_images_u8(3, 91, 4, smooth=True)
-    pil = [Image.fromarray(a.numpy()) for a in big]
+    rng = np.random.default_rng(5)
+    pil = [Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)) for h, w in ((91, 91), (40, 133), (300, 57))]
+    pil.append(Image.fromarray(rng.integers(0, 256, (64, 80), dtype=np.uint8), mode="L"))  # converted to RGB like HF does
+    assert bb.gpu_ingest
     got = bb(pil).cpu()
+    bb.gpu_ingest = False
+    via_hf = bb(pil).cpu()
     pv = proc(images=pil, text="x", return_tensors="pt")["pixel_values"]
     ref = O.tower_features(spec, weights.hf_to_canonical(spec, sd), pv)
     assert torch.nn.functional.cosine_similarity(got, ref).min() >= COS_MIN
+    assert torch.nn.functional.cosine_similarity(via_hf, ref).min() >= COS_MIN
+    assert (got - via_hf).abs().max() <= 2e-3 * ref.abs().max()
 
 
 def test_checkpoint_roundtrip_repacks_weights(cuda_device):

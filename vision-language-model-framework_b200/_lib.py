@@ -72,6 +72,12 @@ SIGNATURES = {
     "vlmfw_tower_hidden_ptr": (_vp, [_vp, _vp]),
     "vlmfw_tower_last_launches": (_i64, [_vp]),
     "vlmfw_tower_forward_host": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "vlmfw_preproc_create": (C.c_int, [_i32, _i32, C.POINTER(_vp)]),
+    "vlmfw_preproc_destroy": (None, [_vp]),
+    "vlmfw_preproc_workspace_bytes": (_sz, [_vp, _vp, _vp, _i32]),
+    "vlmfw_preproc_run": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "vlmfw_preproc_last_launches": (_i64, [_vp]),
+    "vlmfw_resize_weights": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "vlmfw_probe_forward": (C.c_int, [_vp, _i32, _i32, C.POINTER(Head), _i32, _vp, _i32, _vp, _vp]),
     "vlmfw_probe_bn_stats": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "vlmfw_probe_linear_grads": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _vp,

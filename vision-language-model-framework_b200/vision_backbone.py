@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from .engine import TowerEngine
+from .ingest import ImageIngest
 from .specs import ARCH_CLIP, ARCH_EVA, ARCH_SIGLIP, POOL_CLS, POOL_LN_CLS_LN, POOL_LN_MEAN, POOL_MEAN, TowerSpec, \
     spec_from_hf_config
 
@@ -74,6 +75,8 @@ class B200VisionBackbone(VisionBackbone):
             raise ValueError(f"output_dim {output_dim} does not match the tower's hidden size {spec.hidden}")
         self.spec = spec
         self._engines: Dict[tuple, TowerEngine] = {}
+        self._ingest: Dict[str, ImageIngest] = {}
+        self.gpu_ingest = os.environ.get("VLMFW_INGEST", "gpu") != "hf"
         self._weights_version = 0
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed_weights())
 
@@ -110,9 +113,11 @@ class B200VisionBackbone(VisionBackbone):
     def _stage_pixels(self, images: ImagesLike, dev: torch.device) -> torch.Tensor:
         """PIL / list of PIL / uint8 NHWC tensor / float NCHW ``pixel_values`` -> device tensor the engine accepts.
 
-        Native-size RGB input ships as uint8 (4x fewer H2D bytes than the fp32 ``pixel_values`` the reference copies,
-        models/paligemma.py:108) and the rescale + normalize of the HF processor is fused into the patch gather.
-        Anything else goes through the unchanged HF processor (CPU bicubic resize / crop).
+        Images ship as raw uint8 (4x fewer H2D bytes than the fp32 ``pixel_values`` the reference copies,
+        models/paligemma.py:108); the rescale + normalize of the HF processor is fused into the patch gather, and
+        images that are not already S x S are resized / cropped on the GPU by ``ingest.ImageIngest`` — bit-exact with
+        the processor's own uint8 resize. ``gpu_ingest = False`` (or VLMFW_INGEST=hf) keeps the unchanged HF processor
+        call for such images instead (CPU bicubic resize, fp32 NCHW ingest).
         """
         s = self.spec.image_size
         if isinstance(images, torch.Tensor):
@@ -141,6 +146,11 @@ class B200VisionBackbone(VisionBackbone):
             for i, im in enumerate(lst):
                 arr[i] = np.asarray(im)
             return host.to(dev, non_blocking=True)
+        if self.gpu_ingest:
+            key = str(dev)
+            if key not in self._ingest:
+                self._ingest[key] = ImageIngest.for_spec(self.spec, dev)
+            return self._ingest[key](lst)
         kwargs = {"text": self.PROMPT} if self.PROMPT is not None else {}
         inputs = self.processor(images=lst, return_tensors="pt", **kwargs)
         pv = inputs["pixel_values"].to(torch.float32).contiguous()
