@@ -200,6 +200,14 @@ int vlmfw_probe_adamw(float* params, float* exp_avg, float* exp_avg_sq, const fl
 int vlmfw_probe_bn_running_update(float* running_mean, float* running_var, const double* stats, int32_t dim,
                                   int32_t n_global, float momentum, void* stream);
 
+/* ------------------------------------------------------------------ tester sink
+ * Per-task confusion counts of a batch of predictions, accumulated on the device: counts [tasks, classes, classes] int32
+ * (row = ground truth, column = prediction — sklearn.metrics.confusion_matrix as the reference's Evaluator calls it,
+ * datasets_vlm/evaluate_dataset.py:74-97). pred int32 [rows, tasks] (vlmfw_probe_forward's argmax_out), gt int64
+ * [rows, tasks] with -1 = label missing (skipped, evaluate_dataset.py:78); *dropped counts labels outside [0, classes). */
+int vlmfw_confusion_update(const int32_t* pred, const int64_t* gt, int32_t rows, int32_t tasks, int32_t classes,
+                           int32_t* counts, int32_t* dropped, void* stream);
+
 /* ----------------------------------------------------- kernel-level entry points (parity tests, profiling) */
 /* out = epilogue(A[M,K] x W[N,K]^T), fp32 accumulation in TMEM. A (row stride lda) and W (row stride ldw) are both
  * `dtype` (VLMFW_DT_BF16 or VLMFW_DT_F16). VLMFW_EPI_BIAS_BF16 writes act(acc + bias) in that same 16-bit dtype;

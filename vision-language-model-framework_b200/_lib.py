@@ -79,6 +79,7 @@ SIGNATURES = {
     "vlmfw_preproc_last_launches": (_i64, [_vp]),
     "vlmfw_resize_weights": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "vlmfw_probe_forward": (C.c_int, [_vp, _i32, _i32, C.POINTER(Head), _i32, _vp, _i32, _vp, _vp]),
+    "vlmfw_confusion_update": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "vlmfw_probe_bn_stats": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "vlmfw_probe_linear_grads": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _vp,
                                            _vp, _f32, _vp, _vp, _vp, _vp]),
