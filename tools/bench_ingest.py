@@ -55,7 +55,7 @@ def main():
     bytes_alg = host.numel() + out.numel()
     peak = 6549.8
     try:
-        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbps"]
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
     line = {"kernel": "vlmfw_preproc_run (resize_rows + resize_cols)", "tower": a.tower, "batch": a.batch,

@@ -47,12 +47,12 @@ def pack_images(images: Sequence) -> Tuple[torch.Tensor, np.ndarray, np.ndarray,
     Every image starts at a 16-byte aligned offset. Non-RGB PIL images are converted like the processors do."""
     arrays: List[np.ndarray] = []
     for im in images:
-        if hasattr(im, "mode"):  # PIL
+        if isinstance(im, torch.Tensor):
+            a = im.detach().cpu().numpy()
+        elif hasattr(im, "convert"):  # PIL
             if im.mode != "RGB":
                 im = im.convert("RGB")
             a = np.asarray(im)
-        elif isinstance(im, torch.Tensor):
-            a = im.detach().cpu().numpy()
         else:
             a = np.asarray(im)
         if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:

@@ -139,6 +139,8 @@ class B200VisionBackbone(VisionBackbone):
         lst = list(images) if isinstance(images, (list, tuple)) else [images]
         if len(lst) == 0:
             return torch.empty(0, s, s, 3, dtype=torch.uint8, device=dev)
+        if all(isinstance(im, torch.Tensor) and im.dtype == torch.uint8 and tuple(im.shape) == (s, s, 3) for im in lst):
+            return self._stage_pixels(torch.stack(lst), dev)
         native = all(getattr(im, "size", None) == (s, s) and getattr(im, "mode", None) == "RGB" for im in lst)
         if native:
             host = torch.empty(len(lst), s, s, 3, dtype=torch.uint8).pin_memory()
