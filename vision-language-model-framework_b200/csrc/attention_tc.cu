@@ -31,7 +31,7 @@
 namespace vlmfw {
 namespace {
 
-constexpr int TC_THREADS = 192;  // loader warp, MMA warp, 4 softmax warps (TMEM lane quarter = warp % 4)
+constexpr int TC_THREADS = 256;  // warpgroup 0: loader, S issuer, P·V issuer, (idle); warpgroup 1: 4 softmax warps (TMEM lane quarter = warp % 4)
 constexpr int QB = 128;          // query rows per item (= TMEM lanes)
 constexpr int KB = 64;           // keys per block
 #ifndef VLMFW_ATT_NKV
@@ -56,7 +56,12 @@ struct TcCfg {
     static constexpr int KV_BYTES = KV_MAIN + KB * TAIL_ROW;
     static constexpr int P_BYTES = QB * KB * 2;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int FIXED = Q_BYTES + NP * P_BYTES + BAR_BYTES + 1024;
+#ifdef VLMFW_ATT_NOSLACK
+    static constexpr int ALIGN_SLACK = 0;  // dynamic shared memory declared 1024-byte aligned (checked at run time)
+#else
+    static constexpr int ALIGN_SLACK = 1024;
+#endif
+    static constexpr int FIXED = Q_BYTES + NP * P_BYTES + BAR_BYTES + ALIGN_SLACK;
     static constexpr int NKV_FIT = (SMEM_PER_CTA - FIXED) / (2 * KV_BYTES);
     static constexpr int NKV = NKV_FIT < NKV_WANT ? NKV_FIT : NKV_WANT;
     static_assert(NKV >= 2, "K / V rings need two stages");
@@ -71,7 +76,8 @@ struct TcParams {
     int num_items;  // B * H * nq
     float scale_log2;
     int f16;
-    int dbg;  // VLMFW_ATTN_DBG bit mask (bottleneck experiments only): 1 skip exp+P store, 2 skip P·V MMAs, 4 skip S MMAs
+    int dbg;  // VLMFW_ATTN_DBG bit mask (bottleneck experiments only): 1 skip exp+P store, 2 skip P·V MMAs, 4 skip S MMAs,
+              // 8 skip tail-tile loads, 16 / 64 / 128 skip V / K / Q loads, 32 skip the ctx stores
 };
 
 // TMEM columns (256 allocated per CTA): S0 [0,64) S1 [64,128) O [128, 128 + DHP)
@@ -91,14 +97,28 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
+#ifdef VLMFW_ATT_TRACE
+// timeline experiment (variant builds only): CTA 0 logs (clock << 8 | event) per role
+__device__ long long g_att_trace[4][8192];
+#define TR_DECL int tr_n = 0
+#define TR(role, code)                                                            \
+    do {                                                                          \
+        if (blockIdx.x == 0 && tr_n < 8192) g_att_trace[role][tr_n++] = (clock64() << 8) | (code); \
+    } while (0)
+#else
+#define TR_DECL
+#define TR(role, code)
+#endif
+
 template <int DH, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qt,
                     const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_kvt,
-                    const TcParams p) {
+                    const __grid_constant__ CUtensorMap map_o, const TcParams p) {
     using C = TcCfg<DH>;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    if (C::ALIGN_SLACK == 0 && smem != smem_raw) __trap();  // swizzled tiles need the 1024-byte alignment
     uint8_t* sQ = smem;                         // [Q_BYTES]
     uint8_t* sK = sQ + C::Q_BYTES;              // [C::NKV][KV_BYTES]
     uint8_t* sV = sK + C::NKV * C::KV_BYTES;       // [C::NKV][KV_BYTES]
@@ -124,6 +144,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_kv);
+        tma_prefetch_desc(&map_o);
         if (C::TAIL) {
             tma_prefetch_desc(&map_qt);
             tma_prefetch_desc(&map_kvt);
@@ -160,10 +181,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                                   static_cast<int>(gridDim.x)
                             : 0;
 
+    // Register split (setmaxnreg is per warpgroup): the three single-thread roles keep 48 registers, the softmax
+    // warpgroup takes 208 (2 CTAs x (128 x 48 + 128 x 208) = the whole register file).
+    // (the instruction sits at the top of each role's branch so that ptxas allocates per region)
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------ TMA loader
-        // One in-order stream in CONSUMPTION order: the MMA warp issues the scores of block s before P·V of block
-        // s - 1, so K runs one block ahead of V — a V slot that frees late (after its P·V) never holds up a K load.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        // One in-order stream in CONSUMPTION order: the scores of block s are issued before P·V of block s - 1, so K
+        // runs one block ahead of V — a V slot that frees late (after its P·V) never holds up a K load.
         if (lane == 0) {
             const int T = n_local * J;
             auto coords = [&](int s, int& b, int& h, int& j, int& qb) {
@@ -174,36 +199,51 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 h = (item / p.nq) % p.H;
                 b = item / (p.nq * p.H);
             };
+            TR_DECL;
             for (int s = 0; s <= T; ++s) {
                 int b, h, j, qb;
                 if (s < T) {
                     coords(s, b, h, j, qb);
                     if (j == 0) {
                         const int k = s / J;
+                        TR(0, 1);
                         mbar_wait(q_empty, (k & 1) ^ 1);
-                        mbar_arrive_expect_tx(q_full, C::Q_BYTES);
-                        tma_load_5d(sQ, &map_q, q_full, 0, h, 0, qb * QB, b);
-                        if (C::TAIL) tma_load_5d(sQ + C::Q_MAIN, &map_qt, q_full, 64, h, 0, qb * QB, b);
+                        TR(0, 2);
+                        const bool ld = !(p.dbg & 128), ldt = C::TAIL && ld && !(p.dbg & 8);
+                        mbar_arrive_expect_tx(q_full, (ld ? C::Q_MAIN : 0) + (ldt ? C::Q_BYTES - C::Q_MAIN : 0));
+                        if (ld) tma_load_5d(sQ, &map_q, q_full, 0, h, 0, qb * QB, b);
+                        if (ldt) tma_load_5d(sQ + C::Q_MAIN, &map_qt, q_full, 64, h, 0, qb * QB, b);
                     }
                     const int st = s % C::NKV;
+                    TR(0, 3);
                     mbar_wait(&k_empty[st], ((s / C::NKV) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&k_full[st], C::KV_BYTES);
-                    tma_load_5d(sK + st * C::KV_BYTES, &map_kv, &k_full[st], 0, h, 1, j * KB, b);
-                    if (C::TAIL) tma_load_5d(sK + st * C::KV_BYTES + C::KV_MAIN, &map_kvt, &k_full[st], 64, h, 1, j * KB, b);
+                    TR(0, 4);
+                    const bool ld = !(p.dbg & 64), ldt = C::TAIL && ld && !(p.dbg & 8);
+                    mbar_arrive_expect_tx(&k_full[st], (ld ? C::KV_MAIN : 0) + (ldt ? C::KV_BYTES - C::KV_MAIN : 0));
+                    if (ld) tma_load_5d(sK + st * C::KV_BYTES, &map_kv, &k_full[st], 0, h, 1, j * KB, b);
+                    if (ldt) tma_load_5d(sK + st * C::KV_BYTES + C::KV_MAIN, &map_kvt, &k_full[st], 64, h, 1, j * KB, b);
                 }
                 if (s >= 1) {
                     const int sv = s - 1;
                     coords(sv, b, h, j, qb);
                     const int st = sv % C::NKV;
+                    TR(0, 5);
                     mbar_wait(&v_empty[st], ((sv / C::NKV) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&v_full[st], C::KV_BYTES);
-                    tma_load_5d(sV + st * C::KV_BYTES, &map_kv, &v_full[st], 0, h, 2, j * KB, b);
-                    if (C::TAIL) tma_load_5d(sV + st * C::KV_BYTES + C::KV_MAIN, &map_kvt, &v_full[st], 64, h, 2, j * KB, b);
+                    TR(0, 6);
+                    const bool ld = !(p.dbg & 16), ldt = C::TAIL && ld && !(p.dbg & 8);
+                    mbar_arrive_expect_tx(&v_full[st], (ld ? C::KV_MAIN : 0) + (ldt ? C::KV_BYTES - C::KV_MAIN : 0));
+                    if (ld) tma_load_5d(sV + st * C::KV_BYTES, &map_kv, &v_full[st], 0, h, 2, j * KB, b);
+                    if (ldt) tma_load_5d(sV + st * C::KV_BYTES + C::KV_MAIN, &map_kvt, &v_full[st], 64, h, 2, j * KB, b);
                 }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------------------------------ MMA issuer
+    } else if (warp == 1 || warp == 2) {
+        // ------------------------------------------------------------------------------------------ MMA issuers
+        // TWO single-thread issuers: warp 1 the scores S_t = Q K_t^T, warp 2 the products O += P_t V_t. One thread doing
+        // both spent ~4200 cycles per key block in issue + commit instructions alone (timeline trace: a tcgen05.mma of
+        // this size costs ~80 cycles to issue, a commit ~150) and was the critical path; the two streams only meet
+        // through the softmax warps' barriers, so they need no ordering between them.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         if (lane == 0) {
             constexpr bool f16 = F16;
             const uint32_t idesc_pv = umma_idesc_16_bmn(QB, 64, f16);
@@ -217,11 +257,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             };
             // The key blocks of all of this CTA's items form one stream t = 0 .. T-1 (item t / J, block t % J)
             const int T = n_local * J;
+            TR_DECL;
             auto issue_s = [&](int t) {
                 const int k = t / J, j = t - k * J, st = t % C::NKV, sb = t & 1;
+                TR(1, 1);
                 if (j == 0) mbar_wait(q_full, k & 1);
+                TR(1, 2);
                 mbar_wait(&k_full[st], (t / C::NKV) & 1);
+                TR(1, 3);
                 mbar_wait(&s_empty[sb], ((t >> 1) & 1) ^ 1);
+                TR(1, 4);
                 tc_fence_after();
                 if (!(p.dbg & 4)) {
                     const uint32_t d = tmem_base + TM_S + sb * KB;
@@ -243,14 +288,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             };
             auto issue_pv = [&](int t) {
                 const int k = t / J, j = t - k * J, st = t % C::NKV, pb = t % NP;
+                TR(3, 5);
                 mbar_wait(&v_full[st], (t / C::NKV) & 1);
+                TR(3, 6);
                 mbar_wait(&p_full[pb], (t / NP) & 1);
+                TR(3, 7);
                 if (j == 0) mbar_wait(o_empty, (k & 1) ^ 1);
+                TR(3, 8);
                 tc_fence_after();
                 if (!(p.dbg & 2)) {
                     const uint32_t d = tmem_base + TM_O;
                     const uint32_t a0 = p_u32 + pb * C::P_BYTES, b0 = v_u32 + st * C::KV_BYTES;
                     const int ksteps = kcols_of(j) >> 4;  // 16 keys per step
+#ifndef VLMFW_ATT_PV_INTERLEAVED
+                    // all main-tile MMAs, then all tail-tile MMAs: the two have different instruction descriptors
+                    // (N = 64 / N = TAIL) and the pipe takes a descriptor switch badly when they alternate
+#pragma unroll 1
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t ad = umma_desc_sw128(a0) + 2 * ks;
+                        // V main tile: token-major rows of 128 B (64 head_dim columns) = MN-major SWIZZLE_128B operand;
+                        // 8-key groups are 1024 B apart, one K-step (16 keys) = 2048 B
+                        const uint64_t bd = umma_desc(b0 + ks * 2048, 16, 1024, 2);
+                        umma_bf16_ss(d, ad, bd, idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    if (C::TAIL) {
+#pragma unroll 1
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t ad = umma_desc_sw128(a0) + 2 * ks;
+                            const uint64_t bt = umma_desc(b0 + C::KV_MAIN + ks * 16 * C::TAIL_ROW, 16, 8 * C::TAIL_ROW,
+                                                          C::TAIL_LAYOUT);
+                            umma_bf16_ss(d + 64, ad, bt, idesc_pvt, (j > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    }
+#else
 #pragma unroll 1
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const uint64_t ad = umma_desc_sw128(a0) + 2 * ks;
@@ -264,24 +334,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                             umma_bf16_ss(d + 64, ad, bt, idesc_pvt, (j > 0 || ks > 0) ? 1u : 0u);
                         }
                     }
+#endif
                 }
+                TR(3, 9);
                 umma_commit(&p_empty[pb]);
                 umma_commit(&v_empty[st]);
                 if (j == J - 1) umma_commit(o_full);
             };
-            if (T > 0) issue_s(0);
-            for (int t = 0; t < T; ++t) {
-                // next block's scores first (they keep the softmax warps fed) — unless that block opens the next item
-                // and its Q tile has not landed yet: then this item's P·V (and with it the epilogue) must not wait
-                bool s_first = t + 1 < T;
-                if (s_first && (t + 1) % J == 0) s_first = mbar_test(q_full, ((t + 1) / J) & 1);
-                if (s_first) issue_s(t + 1);
-                issue_pv(t);
-                if (!s_first && t + 1 < T) issue_s(t + 1);
+            if (warp == 1) {
+                for (int t = 0; t < T; ++t) issue_s(t);
+            } else {
+                for (int t = 0; t < T; ++t) issue_pv(t);
             }
         }
+    } else if (warp == 3) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     } else {
         // ------------------------------------------------------------------------------------------ softmax warps
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -290,6 +360,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const uint32_t sw = static_cast<uint32_t>(row) & 7u;
         const float sc = p.scale_log2;
         int t = 0;  // key blocks processed by this CTA
+        bool store_pending = false;
+        static_assert(NP == 2 && 16 * DH * 2 <= 4096, "ctx staging uses this warp's rows of both P tiles");
+#ifdef VLMFW_ATT_TRACE
+        int tr_n = (warp == 4 && lane == 0) ? 0 : 8192;
+#endif
         for (int it = 0; it < n_local; ++it) {
             const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
             const int qb = item % p.nq;
@@ -299,12 +374,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             // warps whose 32 rows all lie past the last token (ragged last query block: EVA 257, CLIP 577) keep the
             // barrier protocol but skip the TMEM reads and the arithmetic
             const bool warp_live = qb * QB + quarter * 32 < p.S;
+            const bool warp_live_q = warp_live;
             float m = 0.f, l = 0.f;
             for (int j = 0; j < J; ++j, ++t) {
                 const int sb = t & 1;
                 const int valid = p.S - j * KB;
                 const int nch = valid >= KB ? 4 : (valid + 15) >> 4;  // 16-key chunks of this block
+                TR(2, 1);
                 mbar_wait(&s_full[sb], (t >> 1) & 1);
+                TR(2, 2);
                 tc_fence_after();
                 uint32_t v[KB];
                 const uint32_t s_addr = lane_base + TM_S + sb * KB;
@@ -314,6 +392,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         if (c < nch) tmem_ld_32x16(s_addr + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[c * 16]));
                     tmem_ld_wait();
                 }
+                TR(2, 3);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_empty[sb]);
@@ -374,9 +453,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     tmem_st_wait();
                     l *= factor;
                 }
+                if (store_pending) {  // the previous item's ctx store still reads this warp's slabs of the P tiles
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                    store_pending = false;
+                }
                 // this P tile was last read by P·V NP blocks ago
                 const int pb = t % NP;
+                TR(2, 4);
                 mbar_wait(&p_empty[pb], ((t / NP) & 1) ^ 1);
+                TR(2, 5);
                 if (!(p.dbg & 1)) {
                     float sum[4] = {0.f, 0.f, 0.f, 0.f};
                     const float neg_m = -m;
@@ -408,13 +494,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     }
                     l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
                 }
+                TR(2, 6);
                 fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[pb]);
+                TR(2, 7);
             }
             // ---- epilogue: O / l -> 16-bit -> ctx[b, tok, h*dh : (h+1)*dh]
+            TR(2, 8);
             mbar_wait(o_full, it & 1);
+            TR(2, 9);
             tc_fence_after();
             uint32_t o[C::DHP];
 #pragma unroll
@@ -423,23 +513,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             tc_fence_before();  // O is in registers: hand the accumulator back to the MMA warp
             __syncwarp();
             if (lane == 0) mbar_arrive(o_empty);
-            if (tok < p.S) {
+            if (warp_live_q && !(p.dbg & 32)) {
+                // O / l -> 16-bit -> this warp's staging slabs (its own 32 rows of the two P tiles, free once the item's
+                // last P·V has completed) -> two 16-row TMA stores into ctx[b, tok, h, :] (rows past S are clipped).
+                // Row-strided 16-byte global stores from registers cost ~2300 cycles per item here (timeline trace).
                 const float inv = 1.f / l;
-                uint16_t* orow = static_cast<uint16_t*>(p.out) + (static_cast<size_t>(b) * p.S + tok) * p.D + h * DH;
+                const uint32_t slab = smem_u32(sP) + (lane >> 4) * C::P_BYTES + quarter * 4096;
+                const uint32_t dst = slab + (lane & 15) * (DH * 2);
+                // head_dim 64: rows are exactly 128 B, every lane would hit the same banks — that map is 128B-swizzled
+                // (chunk c of row r at c ^ (r & 7)); 144- / 176-byte rows spread over the banks by themselves
+                const uint32_t osw = DH == 64 ? (static_cast<uint32_t>(lane) & 7u) : 0u;
 #pragma unroll
-                for (int c = 0; c < C::DHP / 8; ++c) {
-                    if (c * 8 < DH) {
-                        uint32_t w[4];
+                for (int c = 0; c < DH / 8; ++c) {
+                    uint32_t w[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float x0 = __uint_as_float(o[c * 8 + 2 * i]) * inv, x1 = __uint_as_float(o[c * 8 + 2 * i + 1]) * inv;
-                            w[i] = pack_16x2<F16>(x0, x1);
-                        }
-                        *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                    for (int i = 0; i < 4; ++i) {
+                        const float x0 = __uint_as_float(o[c * 8 + 2 * i]) * inv, x1 = __uint_as_float(o[c * 8 + 2 * i + 1]) * inv;
+                        w[i] = pack_16x2<F16>(x0, x1);
                     }
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((static_cast<uint32_t>(c) ^ osw) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                                 "r"(w[3])
+                                 : "memory");
                 }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    const int tok0 = qb * QB + quarter * 32;
+                    tma_store_4d(&map_o, smem_u32(sP) + quarter * 4096, 0, h, tok0, b);
+                    tma_store_4d(&map_o, smem_u32(sP) + C::P_BYTES + quarter * 4096, 0, h, tok0 + 16, b);
+                    tma_store_commit();
+                }
+                store_pending = true;
             }
         }
+        if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -453,28 +560,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 // ------------------------------------------------------------------------------------------------ host side
 struct MapKey {
     const void* ptr;
+    const void* out;
     int B, S, H, dh, f16;
     bool operator==(const MapKey& o) const {
-        return ptr == o.ptr && B == o.B && S == o.S && H == o.H && dh == o.dh && f16 == o.f16;
+        return ptr == o.ptr && out == o.out && B == o.B && S == o.S && H == o.H && dh == o.dh && f16 == o.f16;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
-        size_t h = reinterpret_cast<size_t>(k.ptr);
+        size_t h = reinterpret_cast<size_t>(k.ptr) * 31u ^ reinterpret_cast<size_t>(k.out);
         for (int v : {k.B, k.S, k.H, k.dh, k.f16}) h = h * 1000003u ^ static_cast<size_t>(v);
         return h;
     }
 };
 struct MapSet {
-    CUtensorMap q, qt, kv, kvt;
+    CUtensorMap q, qt, kv, kvt, o;
 };
 
 template <int DH>
-int get_maps(const void* qkv, bool f16, int B, int S, int H, MapSet* out) {
+int get_maps(const void* qkv, const void* ctx, bool f16, int B, int S, int H, MapSet* out) {
     using C = TcCfg<DH>;
     static std::mutex mu;
     static std::unordered_map<MapKey, MapSet, MapKeyHash> cache;
-    MapKey key{qkv, B, S, H, DH, f16 ? 1 : 0};
+    MapKey key{qkv, ctx, B, S, H, DH, f16 ? 1 : 0};
     {
         std::lock_guard<std::mutex> lk(mu);
         auto it = cache.find(key);
@@ -492,6 +600,15 @@ int get_maps(const void* qkv, bool f16, int B, int S, int H, MapSet* out) {
     MapSet ms;
     int rc = encode_tensor_map(&ms.q, f16, 5, qkv, dims, strides, box_q, 128);
     if (rc != VLMFW_OK) return rc;
+    {
+        // ctx [B, S, H, dh]: 16-row x dh boxes; dense rows in shared memory, 128B-swizzled when a row is exactly 128 B
+        const uint64_t odims[4] = {static_cast<uint64_t>(DH), static_cast<uint64_t>(H), static_cast<uint64_t>(S),
+                                   static_cast<uint64_t>(B)};
+        const uint64_t ostrides[3] = {static_cast<uint64_t>(DH) * 2, D * 2, static_cast<uint64_t>(S) * D * 2};
+        const uint32_t obox[4] = {static_cast<uint32_t>(DH), 1, 16, 1};
+        rc = encode_tensor_map(&ms.o, f16, 4, ctx, odims, ostrides, obox, DH == 64 ? 128 : 0);
+        if (rc != VLMFW_OK) return rc;
+    }
     rc = encode_tensor_map(&ms.kv, f16, 5, qkv, dims, strides, box_kv, 128);
     if (rc != VLMFW_OK) return rc;
     if (C::TAIL) {
@@ -519,7 +636,7 @@ int launch_tc(const void* qkv, int batch, int tokens, int heads, void* out, int 
     using C = TcCfg<DH>;
     constexpr bool f16 = F16;
     MapSet ms;
-    int rc = get_maps<DH>(qkv, f16, batch, tokens, heads, &ms);
+    int rc = get_maps<DH>(qkv, out, f16, batch, tokens, heads, &ms);
     if (rc != VLMFW_OK) return rc;
     auto kern = attention_tc_kernel<DH, F16>;
     static bool attr_set = false;
@@ -544,12 +661,18 @@ int launch_tc(const void* qkv, int batch, int tokens, int heads, void* out, int 
     }
     const int slots = 2 * num_sms();
     const int grid = p.num_items < slots ? p.num_items : slots;
-    kern<<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(ms.q, ms.qt, ms.kv, ms.kvt, p);
+    kern<<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(ms.q, ms.qt, ms.kv, ms.kvt, ms.o, p);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
 
 }  // namespace
+
+#ifdef VLMFW_ATT_TRACE
+extern "C" int vlmfw_debug_att_trace(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_att_trace, sizeof(g_att_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // head_dim 64 / 72 / 88 (the three towers) run on tcgen05; returns 1 when the shape is not covered (caller falls back to
 // the generic mma.sync kernel of attention.cu, which takes any head_dim % 8 == 0 up to 96).
