@@ -197,6 +197,22 @@ int vlmfw_probe_linear_grads(const float* x, const int64_t* targets, int32_t bat
 int vlmfw_probe_adamw(float* params, float* exp_avg, float* exp_avg_sq, const float* bucket, int64_t numel,
                       int64_t weight_sum_index, int32_t step, float lr, float beta1, float beta2, float eps,
                       float weight_decay, void* stream);
+/* Deeper head (base_probe.py:14-22: BatchNorm1d -> Dropout -> Linear(D,Hd) -> GELU(erf) -> Dropout -> Linear(Hd,C)) and the
+ * multitask step (multitask_trainer.py:188-263): same phase contract as the linear head. `params` is the head's flat
+ * parameter vector [W1 (Hd*D) | b1 (Hd) | W2 (C*Hd) | b2 (C) | gamma (D) | beta (D)], `bucket` has that layout followed by
+ * [loss_sum, weight_sum], all un-normalised sums over the local rows. keep1 uint8 [B,D], keep2 uint8 [B,Hd] (or NULL).
+ * scratch: vlmfw_probe_deep_scratch_floats(...) floats. A multitask step calls this (or vlmfw_probe_linear_grads) once per
+ * head on the shared statistics, all-reduces the concatenated buckets once, then updates every head with
+ * vlmfw_probe_adamw_ex, whose gradient is grad_scale * bucket / weight_sum (grad_scale = the task's loss weight) and which
+ * leaves a head untouched when no row of the global batch carried its label. */
+size_t vlmfw_probe_deep_scratch_floats(int32_t batch, int32_t dim, int32_t hidden, int32_t classes);
+int vlmfw_probe_deep_grads(const float* x, const int64_t* targets, int32_t batch, int32_t dim, int32_t hidden,
+                           int32_t classes, const double* stats, int32_t n_global, float bn_eps, const float* params,
+                           const float* class_weight, const uint8_t* keep1, const uint8_t* keep2, float dropout_p,
+                           float* bucket, float* logits_out, float* scratch, void* stream);
+int vlmfw_probe_adamw_ex(float* params, float* exp_avg, float* exp_avg_sq, const float* bucket, int64_t numel,
+                         int64_t weight_sum_index, float grad_scale, int32_t step, float lr, float beta1, float beta2,
+                         float eps, float weight_decay, void* stream);
 int vlmfw_probe_bn_running_update(float* running_mean, float* running_var, const double* stats, int32_t dim,
                                   int32_t n_global, float momentum, void* stream);
 

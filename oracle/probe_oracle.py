@@ -82,3 +82,51 @@ def phase2_bucket(x, y, stats, n_global, gamma, beta, weight, bias, class_weight
     dz = dl @ weight.double()
     dy = dz * kp
     return torch.cat([(dl.t() @ z).flatten(), dl.sum(0), (dy * xh).sum(0), dy.sum(0), loss_b.sum()[None], wy.sum()[None]])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Multitask / deeper-head step: probing/train/multitask_trainer.py:188-263 over base_trainer.py:166-181, heads from
+# probing/models/base_probe.py:7-22, run with torch's own modules and autograd in fp64.
+def make_reference_head_any(dim: int, classes: int, hidden: int, dropout_p: float, state: Dict[str, torch.Tensor]):
+    if hidden:
+        head = nn.Sequential(nn.BatchNorm1d(dim), _MaskedDropout(dropout_p), nn.Linear(dim, hidden), nn.GELU(),
+                             _MaskedDropout(dropout_p), nn.Linear(hidden, classes))
+    else:
+        head = nn.Sequential(nn.BatchNorm1d(dim), _MaskedDropout(dropout_p), nn.Linear(dim, classes))
+    head.load_state_dict(state, strict=True)
+    return head.double()
+
+
+def reference_multitask_steps(states: Dict[str, Dict[str, torch.Tensor]], tasks: Dict[str, int], hidden: int, batches,
+                              dropout_p: float, class_weights: Dict[str, Optional[torch.Tensor]],
+                              task_weights: Dict[str, float], lr=1e-4, weight_decay=1e-4):
+    """batches = [(x [B,D], y [B,T], masks [(keep1, keep2 or None) per task]), ...]; the loss of a task is the
+    class-weighted CE over its labelled rows (``criterions[t](logit[mask], target[mask])``), the step minimises
+    ``sum_t w_t loss_t`` (``reduce_losses``) with one AdamW over all heads. Returns ({task: state}, [{task: loss}])."""
+    dim = next(iter(states.values()))["0.weight"].shape[0]
+    heads = nn.ModuleDict({t: make_reference_head_any(dim, c, hidden, dropout_p, states[t]) for t, c in tasks.items()}).train()
+    crit = {t: nn.CrossEntropyLoss(weight=None if class_weights.get(t) is None else class_weights[t].double())
+            for t in tasks}
+    opt = torch.optim.AdamW(heads.parameters(), lr=lr, weight_decay=weight_decay)
+    history = []
+    for x, y, masks in batches:
+        opt.zero_grad(set_to_none=True)
+        total, losses = None, {}
+        for i, t in enumerate(tasks):
+            heads[t][1].keep = masks[i][0]
+            if hidden:
+                heads[t][4].keep = masks[i][1]
+            logits = heads[t](x.double())
+            m = y[:, i] != -1
+            if m.any():
+                lt = crit[t](logits[m], y[m, i])
+                losses[t] = float(lt.detach())
+                total = task_weights[t] * lt if total is None else total + task_weights[t] * lt
+            else:
+                losses[t] = None
+        if total is not None:
+            total.backward()
+            opt.step()
+        history.append(losses)
+    out = {t: {k: (v.float() if v.is_floating_point() else v) for k, v in heads[t].state_dict().items()} for t in tasks}
+    return out, history

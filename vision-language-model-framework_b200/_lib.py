@@ -84,6 +84,10 @@ SIGNATURES = {
     "vlmfw_probe_linear_grads": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _vp,
                                            _vp, _f32, _vp, _vp, _vp, _vp]),
     "vlmfw_probe_adamw": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "vlmfw_probe_deep_scratch_floats": (_sz, [_i32, _i32, _i32, _i32]),
+    "vlmfw_probe_deep_grads": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _f32,
+                                         _vp, _vp, _vp, _vp]),
+    "vlmfw_probe_adamw_ex": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _i32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "vlmfw_probe_bn_running_update": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, _vp]),
     "vlmfw_gemm_tn": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
                                 _i32, _i32, _i32, _i32, _i32, _vp]),

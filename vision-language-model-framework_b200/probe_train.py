@@ -160,3 +160,220 @@ class ProbeTrainStep:
         allreduce_sum_(self.phase1_stats(x), self.group)
         allreduce_sum_(self.phase2_grads(x, y, n_global, keep_mask), self.group)
         return self.phase3_update(n_global)
+
+
+class _HeadState:
+    """Flat fp32 parameters / AdamW moments / BatchNorm running statistics of one head.
+    linear: [W (C*D) | b (C) | gamma (D) | beta (D)]; deeper: [W1 (Hd*D) | b1 (Hd) | W2 (C*Hd) | b2 (C) | gamma | beta]."""
+
+    def __init__(self, dim: int, classes: int, hidden: int, device, gen: torch.Generator):
+        self.dim, self.classes, self.hidden = dim, classes, hidden
+        if hidden:
+            self.segments = [("2.weight", hidden * dim, (hidden, dim)), ("2.bias", hidden, (hidden,)),
+                             ("5.weight", classes * hidden, (classes, hidden)), ("5.bias", classes, (classes,))]
+        else:
+            self.segments = [("2.weight", classes * dim, (classes, dim)), ("2.bias", classes, (classes,))]
+        self.segments += [("0.weight", dim, (dim,)), ("0.bias", dim, (dim,))]
+        self.n_params = sum(n for _, n, _ in self.segments)
+        self.params = torch.zeros(self.n_params, device=device)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.running_mean = torch.zeros(dim, device=device)
+        self.running_var = torch.ones(dim, device=device)
+        self.num_batches_tracked = 0
+        # nn.Linear default init (uniform +-1/sqrt(fan_in)), BatchNorm1d weight 1 / bias 0, seeded
+        for name, _, shape in self.segments:
+            v = self.view(name)
+            if name == "0.weight":
+                v.fill_(1.0)
+            elif name != "0.bias":
+                fan_in = dim if name.startswith("2.") else hidden
+                v.copy_((torch.rand(shape, generator=gen) * 2 - 1) / fan_in ** 0.5)
+
+    def view(self, name: str) -> torch.Tensor:
+        off = 0
+        for key, n, shape in self.segments:
+            if key == name:
+                return self.params[off: off + n].view(shape)
+            off += n
+        raise KeyError(name)
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str = "") -> None:
+        for name, _, _ in self.segments:
+            self.view(name).copy_(sd[prefix + name])
+        self.running_mean.copy_(sd[prefix + "0.running_mean"])
+        self.running_var.copy_(sd[prefix + "0.running_var"])
+        self.num_batches_tracked = int(sd.get(prefix + "0.num_batches_tracked", 0))
+
+    def state_dict(self, prefix: str = "") -> Dict[str, torch.Tensor]:
+        out = {prefix + name: self.view(name).clone() for name, _, _ in self.segments}
+        out[prefix + "0.running_mean"] = self.running_mean.clone()
+        out[prefix + "0.running_var"] = self.running_var.clone()
+        out[prefix + "0.num_batches_tracked"] = torch.tensor(self.num_batches_tracked)
+        return out
+
+
+class MultiTaskProbeTrainStep:
+    """Train step of a ``MultiTaskProbe`` (or a deeper ``LinearProbe``) on cached features, data parallel.
+
+    Restates the loop body of probing/train/multitask_trainer.py:188-263 over probing/train/base_trainer.py:166-181:
+    every head sees the same features, its cross entropy runs over the rows whose label is present (``-1`` = missing),
+    class-weighted (:162), the total loss is ``sum_t w_t * loss_t`` with static task weights or the inverse EMA of the
+    per-task losses normalised to mean 1 (``_compute_task_weights``, :209-226; recomputed by ``on_epoch_start()``, the EMA
+    fed after every step, :243-263), one AdamW over all head parameters. Heads: ``make_head`` or ``make_head_deeper``
+    (probing/models/base_probe.py:7-22). Phases as in ``ProbeTrainStep``: shared BatchNorm sums -> all-reduce ->
+    per-head gradients into ONE flat bucket -> all-reduce -> AdamW per head with ``grad = w_t * bucket / weight_sum_t``.
+    State-dict keys are the reference's (``heads.<task>.{0,2[,5]}.*``).
+
+    Two deliberate deviations, both only when a task has NO labelled row in a whole global batch: the reference leaves
+    that head's parameters without gradient (skipped by AdamW, its step counter not advanced); here the update is
+    skipped too but the bias-correction step counter is shared by all heads.
+    """
+
+    def __init__(self, dim: int, tasks: Dict[str, int], device="cuda", deeper: bool = False, hidden_dim: int = 512,
+                 lr: float = 1e-4, weight_decay: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 dropout_p: float = 0.3, class_weights: Optional[Dict[str, torch.Tensor]] = None,
+                 task_weights: Optional[Dict[str, float]] = None, use_running_means: bool = False,
+                 ema_alpha: float = 0.99, bn_eps: float = 1e-5, bn_momentum: float = 0.1, seed: int = 0, group=None):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("MultiTaskProbeTrainStep runs on CUDA only: vlmfw_b200 has no CPU fallback")
+        self.dim, self.tasks = dim, dict(tasks)
+        self.hidden = int(hidden_dim) if deeper else 0
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.dropout_p, self.bn_eps, self.bn_momentum = dropout_p, bn_eps, bn_momentum
+        self.seed, self.group = seed, group
+        self._lib = _lib.load()
+        g = torch.Generator().manual_seed(seed)
+        self.heads = {t: _HeadState(dim, c, self.hidden, self.device, g) for t, c in self.tasks.items()}
+        self.class_weights = {t: (None if not class_weights or class_weights.get(t) is None
+                                  else class_weights[t].to(self.device, torch.float32).contiguous()) for t in self.tasks}
+        self.static_task_weights = {t: float((task_weights or {}).get(t, 1.0)) for t in self.tasks}
+        self.use_running_means, self.ema_alpha = use_running_means, ema_alpha
+        self.ema: Dict[str, Optional[float]] = {t: None for t in self.tasks}
+        self.current_task_weights = dict(self.static_task_weights)
+        self.stats = torch.zeros(2 * dim, dtype=torch.float64, device=self.device)
+        sizes = [h.n_params + 2 for h in self.heads.values()]
+        self.bucket = torch.zeros(sum(sizes), device=self.device)
+        self._offsets = [sum(sizes[:i]) for i in range(len(sizes))]
+        self.step_count = 0
+        self.last_logits: Dict[str, torch.Tensor] = {}
+
+    # ---- task weights (multitask_trainer.py:209-226, 235-263) ---------------------------------------------------
+    def on_epoch_start(self) -> Dict[str, float]:
+        if not self.use_running_means:
+            self.current_task_weights = dict(self.static_task_weights)
+        else:
+            raw = [1.0 / max(self.static_task_weights[t] if self.ema[t] is None else float(self.ema[t]), 1e-8)
+                   for t in self.tasks]
+            avg = sum(raw) / max(1, len(raw))
+            self.current_task_weights = {t: raw[i] / avg for i, t in enumerate(self.tasks)}
+        return dict(self.current_task_weights)
+
+    def _update_ema(self, losses: Dict[str, Optional[float]]) -> None:
+        for t, v in losses.items():
+            if v is None or v != v or v in (float("inf"), float("-inf")):
+                continue
+            self.ema[t] = v if self.ema[t] is None else self.ema_alpha * self.ema[t] + (1 - self.ema_alpha) * v
+
+    # ---- state --------------------------------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str = "heads.") -> None:
+        for t, h in self.heads.items():
+            h.load_state_dict(sd, f"{prefix}{t}.")
+
+    def state_dict(self, prefix: str = "heads.") -> Dict[str, torch.Tensor]:
+        out: Dict[str, torch.Tensor] = {}
+        for t, h in self.heads.items():
+            out.update(h.state_dict(f"{prefix}{t}."))
+        return out
+
+    def dropout_keep_masks(self, task_index: int, n_global: int, lo: int, hi: int):
+        """(keep1 [rows, D], keep2 [rows, Hd] or None), keyed by (seed, step, task, GLOBAL row)."""
+        if self.dropout_p <= 0.0:
+            return None, None
+        g = torch.Generator(device="cpu").manual_seed((self.seed * 1000003 + self.step_count) * 131 + task_index)
+        k1 = (torch.rand(n_global, self.dim, generator=g) >= self.dropout_p)[lo:hi]
+        k2 = (torch.rand(n_global, self.hidden, generator=g) >= self.dropout_p)[lo:hi] if self.hidden else None
+        dev = lambda m: None if m is None else m.to(torch.uint8).to(self.device).contiguous()  # noqa: E731
+        return dev(k1), dev(k2)
+
+    # ---- phases -------------------------------------------------------------------------------------------------
+    def phase1_stats(self, x: torch.Tensor) -> torch.Tensor:
+        with torch.cuda.device(x.device):
+            _lib.check(self._lib.vlmfw_probe_bn_stats(x.data_ptr(), x.shape[0], self.dim, self.stats.data_ptr(),
+                                                      torch.cuda.current_stream(x.device).cuda_stream))
+        return self.stats
+
+    def phase2_grads(self, x: torch.Tensor, y: torch.Tensor, n_global: int, masks) -> torch.Tensor:
+        """y int64 [B, T] (task order of ``self.tasks``); masks: list of (keep1, keep2) per task."""
+        b = x.shape[0]
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        yt = y.t().contiguous()  # [T, B]
+        keepalive = [yt]
+        with torch.cuda.device(x.device):
+            for i, (t, h) in enumerate(self.heads.items()):
+                bucket = self.bucket[self._offsets[i]: self._offsets[i] + h.n_params + 2]
+                logits = torch.empty(b, h.classes, device=x.device)
+                self.last_logits[t] = logits
+                k1, k2 = masks[i]
+                cw = self.class_weights[t]
+                if self.hidden:
+                    n = int(self._lib.vlmfw_probe_deep_scratch_floats(b, self.dim, self.hidden, h.classes))
+                    scratch = torch.empty(n, device=x.device)
+                    _lib.check(self._lib.vlmfw_probe_deep_grads(
+                        x.data_ptr(), yt[i].data_ptr(), b, self.dim, self.hidden, h.classes, self.stats.data_ptr(),
+                        n_global, self.bn_eps, h.params.data_ptr(), None if cw is None else cw.data_ptr(),
+                        None if k1 is None else k1.data_ptr(), None if k2 is None else k2.data_ptr(), self.dropout_p,
+                        bucket.data_ptr(), logits.data_ptr(), scratch.data_ptr(), st))
+                else:
+                    scratch = torch.empty(b * (h.classes + 2), device=x.device)
+                    _lib.check(self._lib.vlmfw_probe_linear_grads(
+                        x.data_ptr(), yt[i].data_ptr(), b, self.dim, h.classes, self.stats.data_ptr(), n_global,
+                        self.bn_eps, h.view("0.weight").data_ptr(), h.view("0.bias").data_ptr(),
+                        h.view("2.weight").data_ptr(), h.view("2.bias").data_ptr(),
+                        None if cw is None else cw.data_ptr(), None if k1 is None else k1.data_ptr(), self.dropout_p,
+                        bucket.data_ptr(), logits.data_ptr(), scratch.data_ptr(), st))
+                keepalive += [scratch, k1, k2]
+        self._keepalive = keepalive
+        return self.bucket
+
+    def phase3_update(self, n_global: int) -> Dict[str, Optional[float]]:
+        self.step_count += 1
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            for i, (t, h) in enumerate(self.heads.items()):
+                bucket = self.bucket[self._offsets[i]: self._offsets[i] + h.n_params + 2]
+                _lib.check(self._lib.vlmfw_probe_adamw_ex(
+                    h.params.data_ptr(), h.exp_avg.data_ptr(), h.exp_avg_sq.data_ptr(), bucket.data_ptr(), h.n_params,
+                    h.n_params + 1, float(self.current_task_weights[t]), self.step_count, self.lr, self.betas[0],
+                    self.betas[1], self.eps, self.wd, st))
+                _lib.check(self._lib.vlmfw_probe_bn_running_update(
+                    h.running_mean.data_ptr(), h.running_var.data_ptr(), self.stats.data_ptr(), self.dim, n_global,
+                    self.bn_momentum, st))
+                h.num_batches_tracked += 1
+        # the step's only D2H read: [loss_sum, weight_sum] of every head
+        idx = torch.tensor([o + h.n_params + k for o, h in zip(self._offsets, self.heads.values()) for k in (0, 1)],
+                           device=self.device)
+        tails = self.bucket[idx].tolist()
+        losses = {t: (tails[2 * i] / tails[2 * i + 1] if tails[2 * i + 1] > 0 else None) for i, t in enumerate(self.tasks)}
+        if self.use_running_means:
+            self._update_ema(losses)
+        return losses
+
+    def step(self, x: torch.Tensor, y: torch.Tensor, n_global: Optional[int] = None, global_offset: int = 0,
+             masks=None) -> Dict[str, Optional[float]]:
+        """One optimisation step on this rank's rows: ``x [B_local, D]`` fp32, ``y [B_local, T]`` int64 (-1 = missing).
+        Returns the per-task mean losses over the GLOBAL batch (None where no row carried the label)."""
+        if not x.is_cuda:
+            raise RuntimeError("features must be CUDA tensors")
+        x = x.to(torch.float32).contiguous()
+        y = y.to(device=x.device, dtype=torch.int64)
+        if y.dim() == 1:
+            y = y[:, None]
+        b = x.shape[0]
+        n_global = b if n_global is None else n_global
+        if masks is None:
+            masks = [self.dropout_keep_masks(i, n_global, global_offset, global_offset + b) for i in range(len(self.tasks))]
+        allreduce_sum_(self.phase1_stats(x), self.group)
+        allreduce_sum_(self.phase2_grads(x, y, n_global, masks), self.group)
+        return self.phase3_update(n_global)
