@@ -88,6 +88,40 @@ def test_ragged_batches_and_determinism(cuda_device):
     assert eng.forward(imgs[:0]).shape == (0, spec.hidden)
 
 
+@pytest.mark.parametrize("name,batch,golden", [("siglip_so400m", 256, "siglip_so400m"), ("clip_vit_l_336", 128, "clip_vit_l_336"),
+                                               ("eva_vit_g", 128, "eva_vit_g")])
+def test_full_size_batch_properties(cuda_device, name, batch, golden):
+    """BASELINE.json's full sizes (SigLIP-So400m batch 256, CLIP-L/336 and EVA-g batch 128), where the CPU oracle would take
+    minutes: size-independent properties instead — run-to-run determinism, batch-composition independence (a 256-image
+    forward equals the concatenation of its sub-batches bit for bit: images never interact, tile order never depends
+    on M), the CUDA-graph replay equals the eager launches, and the first images (the golden fixture's seed) still match
+    the reference's own features."""
+    import os
+
+    import numpy as np
+
+    spec = specs.SPECS[name]
+    eng = TowerEngine(spec, "cuda:0")
+    eng.load_hf_state_dict(weights.seeded_hf_state_dict(spec, 1))
+    head = weights.seeded_images_u8(4, spec.image_size, 2, smooth=True)  # the images of tests/golden/<name>.npz
+    rest = torch.randint(0, 256, (batch - 4, spec.image_size, spec.image_size, 3), dtype=torch.uint8,
+                         generator=torch.Generator().manual_seed(3))
+    imgs = torch.cat([head, rest]).cuda()
+    full = eng.forward(imgs).clone()
+    assert torch.isfinite(full).all()
+    assert torch.equal(full, eng.forward(imgs))
+    parts = torch.cat([eng.forward(imgs[lo:lo + 37]).clone() for lo in range(0, batch, 37)])
+    assert torch.equal(full, parts)
+    out = torch.empty_like(full)
+    eng.graphed(imgs, out)()
+    torch.cuda.synchronize()
+    assert torch.equal(full, out)
+    if golden is not None:
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", golden + ".npz"))
+        ref = torch.from_numpy(g["features"])
+        assert torch.nn.functional.cosine_similarity(full[: ref.shape[0]].cpu(), ref).min() >= COS_MIN
+
+
 def test_missing_weight_is_loud(cuda_device):
     from vlmfw_b200._lib import VlmfwError
 
