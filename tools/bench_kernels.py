@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--only", default="")
     ap.add_argument("--no-cublas", action="store_true")
+    ap.add_argument("--dense-ld", action="store_true", help="row pitch = row length (the tower pads 16-bit rows to 128 B)")
     args = ap.parse_args()
     m = args.m
     dev = "cuda"
@@ -44,15 +45,18 @@ def main():
     for name, n, k, kind in shapes:
         if args.only and args.only not in name:
             continue
-        a = (torch.randn(m, k, device=dev) * 0.5).to(DT)
-        w = (torch.randn(n, k, device=dev) / math.sqrt(k)).to(DT)
+        pad = (lambda r, c: torch.empty(r, c, dtype=DT, device=dev)) if args.dense_ld else \
+            (lambda r, c: ops.padded_rows(r, c, DT, dev))
+        a, w = pad(m, k), pad(n, k)
+        a.copy_(torch.randn(m, k, device=dev) * 0.5)
+        w.copy_(torch.randn(n, k, device=dev) / math.sqrt(k))
         bias = torch.randn(n, device=dev)
         flops = 2.0 * m * n * k
         if kind == "resid":
             h = torch.randn(m, n, device=dev)
             fn = lambda: ops.gemm_tn(a, w, bias, resid=h, out=h, block_n=args.block_n)  # noqa: E731
         else:
-            out = torch.empty(m, n, dtype=DT, device=dev)
+            out = pad(m, n)
             act = specs.ACT_GELU_TANH if kind == "gelu" else specs.ACT_NONE
             fn = lambda: ops.gemm_tn(a, w, bias, act=act, out=out, block_n=args.block_n)  # noqa: E731
         med, best = timeit(fn)

@@ -23,7 +23,11 @@ gamma, beta = 1 + rn(D, sc=0.1), rn(D, sc=0.1)
 wqkv, bqkv = rn(3 * D, D, sc=1 / math.sqrt(D)).to(DT), rn(3 * D, sc=0.1)
 wo, bo = rn(D, D, sc=1 / math.sqrt(D)).to(DT), rn(D, sc=0.1)
 w1, b1 = rn(I, D, sc=1 / math.sqrt(D)).to(DT), rn(I, sc=0.1)
-w2, b2 = rn(D, I, sc=1 / math.sqrt(I)).to(DT), rn(D, sc=0.1)
+# fc2's operands with the tower's row pitch (I rounded up to whole 128-byte lines)
+w2 = ops.padded_rows(D, I, DT, dev)
+w2.copy_(rn(D, I, sc=1 / math.sqrt(I)))
+b2 = rn(D, sc=0.1)
+mid = ops.padded_rows(M, I, DT, dev)
 pix = torch.randint(0, 256, (B, 224, 224, 3), device=dev, dtype=torch.uint8, generator=g)
 
 w1f, b1c = ops.ln_fold_weight(rn(I, D, sc=1 / math.sqrt(D)), gamma, beta, b1, dtype=DT)
@@ -36,7 +40,7 @@ for it in range(2):  # the tower's launch sequence for one layer (tower.cu), at 
     qkv = ops.gemm_tn_ln(xn, wqf, bqc, stats, D, 1e-6)
     ctx = ops.attention(qkv, B, spec.tokens, spec.heads, spec.head_dim)
     xn, stats = ops.gemm_tn_resid_stats(ctx, wo, bo, h)
-    mid = ops.gemm_tn_ln(xn, w1f, b1c, stats, D, 1e-6, act=spec.act)
+    ops.gemm_tn_ln(xn, w1f, b1c, stats, D, 1e-6, act=spec.act, out=mid)
     xn, stats = ops.gemm_tn_resid_stats(mid, w2, b2, h)
     pooled = ops.pool(h.view(B, spec.tokens, D), specs.POOL_LN_MEAN, gamma, beta, 1e-6)
     if os.environ.get("VLMFW_PROFILE_CUBLAS") == "1":  # the library GEMM on the fc1 shape, for a side-by-side ncu read

@@ -24,8 +24,8 @@ def _need(t: torch.Tensor, dtype, name: str) -> None:
         raise RuntimeError(f"{name} must be a CUDA tensor: vlmfw_b200 has no CPU fallback")
     if t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
-    if not t.is_contiguous():
-        raise ValueError(f"{name} must be contiguous")
+    if not (t.is_contiguous() or (t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1])):
+        raise ValueError(f"{name} must be contiguous (2-D tensors may have a padded row pitch)")
 
 
 def _dt(t: torch.Tensor, name: str) -> int:
@@ -113,17 +113,28 @@ def ln_fold_weight(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bia
     return w16, c2
 
 
+def padded_rows(rows: int, cols: int, dtype: torch.dtype, device, multiple: int = 64) -> torch.Tensor:
+    """[rows, cols] view whose row pitch is ``cols`` rounded up to ``multiple`` elements — whole 128-byte lines for
+    16-bit data, what the tower uses for its MLP intermediate: TMA box rows then never straddle two lines."""
+    ld = (cols + multiple - 1) // multiple * multiple
+    return torch.empty(rows, ld, dtype=dtype, device=device)[:, :cols]
+
+
 def gemm_tn_ln(a16: torch.Tensor, w16: torch.Tensor, c2: torch.Tensor, stats: torch.Tensor,
-               ln_dim: int, eps: float, *, act: int = ACT_NONE, block_n: int = 0) -> torch.Tensor:
+               ln_dim: int, eps: float, *, act: int = ACT_NONE, block_n: int = 0,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Consumer side of the folded LayerNorm: ``act(rstd (a16 @ w16^T) + c2)`` in a16's dtype."""
     _need(a16, a16.dtype, "a16")
     _need(w16, a16.dtype, "w16")
     _need(stats, torch.float32, "stats")
     m, k = a16.shape
     n = w16.shape[0]
-    out = torch.empty(m, n, dtype=a16.dtype, device=a16.device)
-    d = _lib.GemmDesc(a=a16.data_ptr(), lda=k, w=w16.data_ptr(), ldw=k, dtype=_dt(a16, "a16"), m=m, n=n, k=k,
-                      bias=c2.data_ptr(), epi=EPI_BIAS_BF16, act=act, out=out.data_ptr(), ldo=n, resid=None, ldr=0,
+    if out is None:
+        out = torch.empty(m, n, dtype=a16.dtype, device=a16.device)
+    _need(out, a16.dtype, "out")
+    d = _lib.GemmDesc(a=a16.data_ptr(), lda=a16.stride(0), w=w16.data_ptr(), ldw=w16.stride(0), dtype=_dt(a16, "a16"),
+                      m=m, n=n, k=k, bias=c2.data_ptr(), epi=EPI_BIAS_BF16, act=act, out=out.data_ptr(),
+                      ldo=out.stride(0), resid=None, ldr=0,
                       block_n=block_n, ln_stats=stats.data_ptr(), ln_np=stats.shape[1],
                       ln_dim=ln_dim, ln_eps=eps, h16_out=None, ld_h16=0, stats_out=None)
     with torch.cuda.device(a16.device):
@@ -142,8 +153,8 @@ def gemm_tn_resid_stats(a16: torch.Tensor, w16: torch.Tensor, bias: Optional[tor
     parts = gemm_stats_parts(n, block_n)
     h16 = torch.empty(m, n, dtype=a16.dtype, device=a16.device)
     stats = torch.full((m, parts, 2), float("nan"), dtype=torch.float32, device=a16.device)
-    d = _lib.GemmDesc(a=a16.data_ptr(), lda=k, w=w16.data_ptr(), ldw=k, dtype=_dt(a16, "a16"), m=m, n=n, k=k,
-                      bias=None if bias is None else bias.data_ptr(), epi=EPI_BIAS_RESID_F32, act=ACT_NONE,
+    d = _lib.GemmDesc(a=a16.data_ptr(), lda=a16.stride(0), w=w16.data_ptr(), ldw=w16.stride(0), dtype=_dt(a16, "a16"),
+                      m=m, n=n, k=k, bias=None if bias is None else bias.data_ptr(), epi=EPI_BIAS_RESID_F32, act=ACT_NONE,
                       out=h.data_ptr(), ldo=n, resid=h.data_ptr(), ldr=n, block_n=block_n, ln_stats=None,
                       ln_np=0, ln_dim=0, ln_eps=0.0, h16_out=h16.data_ptr(), ld_h16=n, stats_out=stats.data_ptr())
     with torch.cuda.device(a16.device):
