@@ -25,9 +25,12 @@ def _act_ref(x, act):
     return x
 
 
-# (M, N, K): tile-exact, ragged M, ragged N (4304 = 16*256+208), K % 64 = 16 (4304, 592), tiny
+# (M, N, K): tile-exact, ragged M, ragged N (4304 = 16*256+208), K % 64 = 16 (4304, 592), tiny; the CTA-pair kernel runs a
+# ragged last N tile as a narrower MMA (width rounded up to 16): 1152 -> 128, 4304 -> 208, 1160 -> 144 (8 zero columns),
+# 1288 -> 16 (the narrowest)
 GEMM_SHAPES = [(256, 256, 128), (128, 128, 64), (384, 1152, 1152), (1000, 3456, 1152), (520, 4304, 1152),
-               (520, 1152, 4304), (777, 1152, 592), (64, 144, 144), (130, 432, 144), (40, 176, 384)]
+               (520, 1152, 4304), (777, 1152, 592), (64, 144, 144), (130, 432, 144), (40, 176, 384), (600, 1160, 320),
+               (300, 1288, 192)]
 
 
 # kernel forms: single CTA (128-row tiles) and CTA pair (tcgen05 cta_group::2, 256-row tiles); include/vlmfw_b200.h
@@ -165,7 +168,7 @@ def test_gemm_folded_layernorm_consumer(cuda_device, m, n, k, form, act):
 
 
 @pytest.mark.parametrize("m,n,k", [(384, 1152, 1152), (777, 1152, 4304), (130, 144, 304), (64, 1408, 6144),
-                                   (20000, 1024, 1024)])
+                                   (20000, 1024, 1024), (600, 1160, 320), (300, 1288, 192)])
 @pytest.mark.parametrize("form", ["1cta", "2cta"])
 @pytest.mark.parametrize("block_n", [0, 128, 192, 256])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])

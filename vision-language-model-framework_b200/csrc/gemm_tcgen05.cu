@@ -74,6 +74,11 @@ struct KParams {
     int m, n, k;
     uint32_t idesc;  // tcgen05 instruction descriptor (the operand format is a run-time choice)
     int out_f16;     // 16-bit epilogue output format
+    // ragged last N tile of a CTA-pair GEMM: its real width rounded up to 16 (0 = the last tile is full / feature off) and
+    // the instruction descriptor of that width. SigLIP's N = 1152 = 4.5 tiles: a full-width MMA on a half-empty tile is
+    // 10 % of the kernel's tensor work (and power) spent on zero padding.
+    int tail_n;
+    uint32_t idesc_tail;
     const float* bias;
     void* out;
     int ldo;
@@ -119,7 +124,7 @@ __device__ __forceinline__ float activation(float x) {
 template <int BN, int EPI, int ACT, int CG, bool GEN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                    const __grid_constant__ CUtensorMap tmap_wt, const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const __grid_constant__ CUtensorMap tmap_h16, const KParams p) {
     using C = Cfg<BN, CG, EPI, GEN>;
     extern __shared__ uint8_t smem_raw[];
@@ -149,6 +154,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_wt);
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -186,7 +192,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t phase = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
                 const int m0 = (tile / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM;
-                const int n0 = (tile % n_tiles) * BN + static_cast<int>(cta_rank) * C::B_ROWS;
+                // narrow last tile: each CTA of the pair stages tail_n / 2 rows of W through the narrower box
+                const bool tail = CG == 2 && p.tail_n > 0 && (tile % n_tiles) == n_tiles - 1;
+                const int b_rows = tail ? p.tail_n / 2 : C::B_ROWS;
+                const int n0 = (tile % n_tiles) * BN + static_cast<int>(cta_rank) * b_rows;
+                const uint32_t stage_tx = C::A_BYTES + static_cast<uint32_t>(b_rows) * BK * 2;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -196,9 +206,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     } else if constexpr (CG == 2) {
                         // both CTAs load into their own smem; all bytes are counted on the LEADER's full barrier
                         const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_tx);
                         tma_load_2d_pair(sa, &tmap_a, lead_bar, kb * BK, m0);
-                        tma_load_2d_pair(sb, &tmap_w, lead_bar, kb * BK, n0);
+                        tma_load_2d_pair(sb, tail ? &tmap_wt : &tmap_w, lead_bar, kb * BK, n0);
                     } else {
                         mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
                         tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
@@ -214,12 +224,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0 && cta_rank == 0) {
-            const uint32_t idesc = p.idesc;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const uint32_t idesc =
+                    (CG == 2 && p.tail_n > 0 && (tile % n_tiles) == n_tiles - 1) ? p.idesc_tail : p.idesc;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -403,6 +414,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t box = stg_u32 + b * RES_BOX_BYTES + static_cast<uint32_t>(lane) * (RES_COLS * 4);
                     mbar_wait(&my_bar[b], (q / RES_NBUF) & 1u);
                     tmem_ld_wait();
+                    if (nc >= p.n) {  // warp-uniform: columns a narrow last tile never wrote (stale TMEM) must not reach the row statistics
+#pragma unroll
+                        for (int j = 0; j < RES_COLS; ++j) v[j] = 0u;
+                    }
                     uint32_t hp[RES_COLS / 2];
 #pragma unroll
                     for (uint32_t j = 0; j < RES_COLS / 4; ++j) {
@@ -660,11 +675,23 @@ template <int BN, int EPI, int ACT, int CG, bool GEN>
 int launch_one(const GemmArgs& g, cudaStream_t stream) {
     using C = Cfg<BN, CG, EPI, GEN>;
     const MapDt dt16 = g.f16 ? MAP_F16 : MAP_BF16;
-    CUtensorMap ta, tw, tout, tres, th16;
+    CUtensorMap ta, tw, twt, tout, tres, th16;
     int rc = get_tensor_map(g.a, g.m, g.k, g.lda, BM, BK, dt16, 128, &ta);
     if (rc != VLMFW_OK) return rc;
     rc = get_tensor_map(g.w, g.n, g.k, g.ldw, C::B_ROWS, BK, dt16, 128, &tw);
     if (rc != VLMFW_OK) return rc;
+    twt = tw;
+    int tail_n = 0;
+    if constexpr (CG == 2 && !GEN) {
+        static const bool tail_on = [] { const char* e = getenv("VLMFW_GEMM_TAIL"); return e == nullptr || atoi(e) != 0; }();
+        const int rem = g.n - ((g.n + BN - 1) / BN - 1) * BN;  // real width of the last N tile
+        const int want = (rem + 15) / 16 * 16;
+        if (tail_on && want < BN) {
+            tail_n = want;
+            rc = get_tensor_map(g.w, g.n, g.k, g.ldw, tail_n / 2, BK, dt16, 128, &twt);
+            if (rc != VLMFW_OK) return rc;
+        }
+    }
     tout = ta;  // unused by the generic epilogue, but a kernel parameter must be a valid object
     tres = ta;
     th16 = ta;
@@ -694,6 +721,8 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
     p.n = g.n;
     p.k = g.k;
     p.idesc = umma_idesc_16(BM * CG, BN, g.f16, g.f16);
+    p.tail_n = tail_n;
+    p.idesc_tail = tail_n > 0 ? umma_idesc_16(BM * CG, tail_n, g.f16, g.f16) : p.idesc;
     p.out_f16 = g.f16 ? 1 : 0;
     p.bias = g.bias;
     p.out = g.out;
@@ -735,9 +764,9 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        VLMFW_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tw, tout, tres, th16, p));
+        VLMFW_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tw, twt, tout, tres, th16, p));
     } else {
-        kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tw, tout, tres, th16, p);
+        kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tw, twt, tout, tres, th16, p);
     }
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
