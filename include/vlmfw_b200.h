@@ -129,7 +129,7 @@ void vlmfw_tower_destroy(vlmfw_tower* t);
  *   patch.w [D,3,p,p]  patch.b [D]  cls [D]  pos [S,D]  pre_ln.w/.b [D]  post_ln.w/.b [D]
  *   L<i>.ln1.w/.b  L<i>.qkv.w [3D,D]  L<i>.qkv.b [3D]  L<i>.o.w [D,D]  L<i>.o.b
  *   L<i>.ln2.w/.b  L<i>.fc1.w [I,D]   L<i>.fc1.b [I]   L<i>.fc2.w [D,I] L<i>.fc2.b [D]
- * Matrices are repacked to cfg.compute_dtype (patch K padded 588->592); vectors stay fp32. */
+ * Matrices are repacked to cfg.compute_dtype (patch K padded 588->640: whole 128-byte rows); vectors stay fp32. */
 int vlmfw_tower_set_weight(vlmfw_tower* t, const char* name, const float* src, int64_t numel, void* stream);
 /* 0 when every tensor the configuration needs has been set, else VLMFW_E_STATE (message names the first missing) */
 int vlmfw_tower_ready(vlmfw_tower* t);

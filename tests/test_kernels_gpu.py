@@ -95,6 +95,21 @@ def test_gemm_patch_embed_row_remap(cuda_device, form):
     assert (got[:, 0] == -7.0).all()
 
 
+@pytest.mark.parametrize("form", ["1cta", "2cta", "2cta-generic-epi"])
+@pytest.mark.parametrize("m,n,k,mod", [(700, 432, 304, 64), (1024, 1152, 640, 256), (300, 144, 64, 32)])
+def test_gemm_broadcast_residual(cuda_device, form, m, n, k, mod):
+    """out = A W^T + bias + resid[row % mod] — the position-embedding add of the patch GEMM. With mod a multiple of 32 it
+    runs through the TMA residual epilogue (the residual box is fetched at row % mod), otherwise / when forced through the
+    generic one; both must agree with the reference."""
+    a = _rand((m, k), 24).to(torch.float16)
+    w = _rand((n, k), 25, 1 / math.sqrt(k)).to(torch.float16)
+    bias = _rand((n,), 26, 0.5)
+    pos = _rand((mod, n), 27)
+    out = ops.gemm_tn(a, w, bias, resid=pos, resid_mod=mod, block_n=FORMS[form])
+    ref = a.float() @ w.float().t() + bias + pos.repeat((m + mod - 1) // mod, 1)[:m]
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3)
+
+
 @pytest.mark.parametrize("form", ["1cta", "2cta"])
 def test_gemm_residual_f32_out_of_place(cuda_device, form):
     # resid and out are different buffers with different leading dimensions (two TMA maps)

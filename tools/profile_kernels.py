@@ -35,7 +35,7 @@ wqf, bqc = ops.ln_fold_weight(rn(3 * D, D, sc=1 / math.sqrt(D)), gamma, beta, bq
 parts = ops.gemm_stats_parts(D)
 
 for it in range(2):  # the tower's launch sequence for one layer (tower.cu), at the headline shapes
-    a = ops.im2col(pix, 224, 14, 592, spec.pix_mean, spec.pix_std, dtype=DT)
+    a = ops.im2col(pix, 224, 14, 640, spec.pix_mean, spec.pix_std, dtype=DT)
     xn, stats = ops.row_stats_cast(h, dtype=DT, parts=parts)
     qkv = ops.gemm_tn_ln(xn, wqf, bqc, stats, D, 1e-6)
     ctx = ops.attention(qkv, B, spec.tokens, spec.heads, spec.head_dim)

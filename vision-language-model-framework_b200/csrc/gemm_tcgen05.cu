@@ -388,7 +388,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int t = worker + static_cast<int>(qq / RCHUNKS) * num_workers;
                 const int c = static_cast<int>(qq % RCHUNKS);
                 const int cx = (t % n_tiles) * BN + half * COLS_PER_WARP + c * RES_COLS;
-                const int cy = (t / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
+                int cy = (t / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
+                if (p.resid_mod > 0) cy %= p.resid_mod;  // broadcast residual (position embedding): resid_mod % 32 == 0
                 const uint32_t b = qq % RES_NBUF;
                 mbar_arrive_expect_tx(&my_bar[b], RES_BOX_BYTES);
                 tma_load_2d(stg + b * RES_BOX_BYTES, &tmap_res, &my_bar[b], cx, cy);
@@ -699,7 +700,7 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
         if constexpr (EPI == VLMFW_EPI_BIAS_RESID_F32) {
             rc = get_tensor_map(g.out, g.m, g.n, g.ldo, 32, RES_COLS, MAP_F32, RES_COLS * 4, &tout);
             if (rc != VLMFW_OK) return rc;
-            rc = get_tensor_map(g.resid, g.m, g.n, g.ldr, 32, RES_COLS, MAP_F32, RES_COLS * 4, &tres);
+            rc = get_tensor_map(g.resid, g.resid_mod > 0 ? g.resid_mod : g.m, g.n, g.ldr, 32, RES_COLS, MAP_F32, RES_COLS * 4, &tres);
             if (rc != VLMFW_OK) return rc;
             if (g.h16_out != nullptr) {
                 rc = get_tensor_map(g.h16_out, g.m, g.n, g.ld_h16, 32, 32, dt16, 64, &th16);
@@ -776,7 +777,8 @@ template <int BN, int CG>
 int dispatch_epi(const GemmArgs& g, cudaStream_t stream) {
     // row remap (patch embedding around the class-token slot) and a broadcast residual (position embedding) go through
     // the generic epilogue; everything else moves its output (and residual) with TMA
-    const bool generic = g.grp > 0 || g.resid_mod > 0 || (g.block_n & VLMFW_GEMM_FORCE_GENERIC_EPI);
+    const bool generic = g.grp > 0 || (g.resid_mod > 0 && (g.resid_mod % 32 != 0 || g.epi != VLMFW_EPI_BIAS_RESID_F32)) ||
+                         (g.block_n & VLMFW_GEMM_FORCE_GENERIC_EPI);
     if (g.epi == VLMFW_EPI_BIAS_RESID_F32) {
         if (generic) return launch_one<BN, VLMFW_EPI_BIAS_RESID_F32, VLMFW_ACT_NONE, CG, true>(g, stream);
         return launch_one<BN, VLMFW_EPI_BIAS_RESID_F32, VLMFW_ACT_NONE, CG, false>(g, stream);
@@ -883,7 +885,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
         VLMFW_REQUIRE(g.epi == VLMFW_EPI_BIAS_BF16, "gemm: unknown epilogue %d", g.epi);
     }
     if (g.bias) VLMFW_REQUIRE((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
-    const bool generic_epi = g.grp > 0 || g.resid_mod > 0 || (g.block_n & VLMFW_GEMM_FORCE_GENERIC_EPI);
+    const bool generic_epi = g.grp > 0 || (g.resid_mod > 0 && (g.resid_mod % 32 != 0 || g.epi != VLMFW_EPI_BIAS_RESID_F32)) ||
+                             (g.block_n & VLMFW_GEMM_FORCE_GENERIC_EPI);
     if (g.ln_stats != nullptr) {
         VLMFW_REQUIRE(g.epi == VLMFW_EPI_BIAS_BF16 && !generic_epi, "gemm: folded LayerNorm needs the 16-bit TMA epilogue");
         VLMFW_REQUIRE(g.ln_np > 0 && g.ln_dim > 0, "gemm: folded LayerNorm needs ln_np / ln_dim");

@@ -202,7 +202,8 @@ extern "C" int vlmfw_tower_create(const vlmfw_tower_cfg* cfg, vlmfw_tower** out)
     t->I = cfg->mlp;
     t->L = cfg->layers;
     t->kreal = 3 * cfg->patch_size * cfg->patch_size;
-    t->kpad = static_cast<int>(align_up(t->kreal, 8));
+    // K of the patch GEMM padded to whole 128-byte rows (588 -> 640): operand rows never straddle L2 lines
+    t->kpad = static_cast<int>(align_up(t->kreal, 64));
     t->layers.resize(t->L);
     const int64_t D = t->D, I = t->I;
     t->add_slot("patch.w", &t->patch_w, true, D, t->kreal, t->kpad);
@@ -369,6 +370,7 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
     const int act_dt = t->f16 ? VLMFW_DT_F16 : VLMFW_DT_BF16;
 
     // ---- embeddings: conv-as-GEMM (+bias +position embedding), class token, optional pre-LN
+    bool head_done = false;  // xn / stats of the embeddings already produced by the patch GEMM's epilogue
     rc = launch_im2col(pixels, pix_fmt, batch, t->cfg.image_size, t->cfg.patch_size, t->cfg.pix_mean, t->cfg.pix_std,
                        patch_a, t->kpad, t->f16, st);
     if (rc != VLMFW_OK) return rc;
@@ -388,9 +390,18 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.resid = t->posb;
         g.ldr = D;
         g.resid_mod = P;
-        g.grp = P;
-        g.grp_out = S;
-        g.grp_off = t->cfg.has_cls ? 1 : 0;
+        if (t->cfg.has_cls) {  // rows move over by the class-token slot of every image: generic epilogue
+            g.grp = P;
+            g.grp_out = S;
+            g.grp_off = 1;
+        } else if (!t->cfg.has_pre_ln && P % 32 == 0) {
+            // no row remap: the TMA residual epilogue (broadcast position embedding) also leaves the 16-bit copy and the
+            // row statistics the first QKV GEMM needs — no row_stats_cast launch
+            g.h16_out = xn;
+            g.ld_h16 = D;
+            g.stats_out = stats;
+            head_done = true;
+        }
         rc = launch_gemm(g, st);
         if (rc != VLMFW_OK) return rc;
     }
@@ -404,8 +415,10 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
     }
     // ---- encoder layers (pre-LN transformer blocks). No LayerNorm kernel runs in here: ln1 / ln2 are folded into the
     // QKV / fc1 GEMMs; the out-proj / fc2 epilogues leave the 16-bit copy of h (xn) and its row statistics behind.
-    rc = launch_row_stats_cast(h, M, D, xn, t->f16, stats, np, st);
-    if (rc != VLMFW_OK) return rc;
+    if (!head_done) {
+        rc = launch_row_stats_cast(h, M, D, xn, t->f16, stats, np, st);
+        if (rc != VLMFW_OK) return rc;
+    }
     for (int li = 0; li < t->L; ++li) {
         const LayerW& w = t->layers[li];
         GemmArgs g;
