@@ -175,6 +175,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // the prologue above may overlap the QKV GEMM's tail; qkv is read (and ctx written) only from here on
+    pdl_launch_dependents();
     const int J = p.J;
     const int n_local = static_cast<int>(blockIdx.x) < p.num_items
                             ? (p.num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
@@ -661,7 +663,19 @@ int launch_tc(const void* qkv, int batch, int tokens, int heads, void* out, int 
     }
     const int slots = 2 * num_sms();
     const int grid = p.num_items < slots ? p.num_items : slots;
-    kern<<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(ms.q, ms.qt, ms.kv, ms.kvt, ms.o, p);
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        VLMFW_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ms.q, ms.qt, ms.kv, ms.kvt, ms.o, p));
+    }
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }

@@ -75,6 +75,8 @@ int encode_tensor_map(CUtensorMap* out, bool f16, int rank, const void* ptr, con
                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 int device_check();
+// VLMFW_PDL=0 switches programmatic dependent launch off (A/B timing)
+bool pdl_enabled();
 int num_sms();
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
 // number of (sum, sum of squares) partials per row the residual epilogue writes for an N-column output

@@ -184,6 +184,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Everything above (barriers, TMEM, descriptor prefetch) touched no global data and may overlap the tail of the
+    // previous kernel in the stream; from here on its outputs are read and its inputs overwritten.
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -758,16 +762,28 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
         cfg.blockDim = dim3(GEMM_THREADS);
         cfg.dynamicSmemBytes = C::SMEM_BYTES;
         cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
         VLMFW_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tw, twt, tout, tres, th16, p));
     } else {
-        kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tw, twt, tout, tres, th16, p);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        VLMFW_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tw, twt, tout, tres, th16, p));
     }
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
@@ -861,6 +877,11 @@ int encode_tensor_map(CUtensorMap* out, bool f16, int rank, const void* ptr, con
         return VLMFW_E_CUDA;
     }
     return VLMFW_OK;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("VLMFW_PDL"); return e == nullptr || atoi(e) != 0; }();
+    return on;
 }
 
 int gemm_stats_parts(int n, int block_n) {
