@@ -9,7 +9,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from vlmfw_b200 import probes, specs, weights  # noqa: E402
 from vlmfw_b200.vision_backbone import backbone_from_spec  # noqa: E402

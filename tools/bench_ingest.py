@@ -66,9 +66,16 @@ def main():
     try:
         from PIL import Image
 
-        from oracle import hf_ref
+        import transformers as tf
 
-        proc = hf_ref.build_hf_processor(spec)
+        # the processor the reference's adapters call, built offline with the checkpoint's constants
+        size, kw = spec.image_size, dict(image_mean=list(spec.pix_mean), image_std=list(spec.pix_std))
+        if spec.arch == specs.ARCH_CLIP:
+            proc = tf.CLIPImageProcessor(size={"shortest_edge": size}, crop_size={"height": size, "width": size}, **kw)
+        elif spec.arch == specs.ARCH_SIGLIP:
+            proc = tf.SiglipImageProcessor(size={"height": size, "width": size}, resample=3, **kw)
+        else:
+            proc = tf.BlipImageProcessor(size={"height": size, "width": size}, **kw)
         pil = [Image.fromarray(x) for x in imgs[: a.cpu_images]]
         proc(images=pil[:4], return_tensors="pt")
         t0 = time.perf_counter()
