@@ -279,17 +279,21 @@ def run_b200_arm(args):
                                torch.randn(spec.mlp, device=dev), dtype=tdt)
     del x
     o = ops.padded_rows(M, spec.mlp, tdt, dev)  # the tower's own row pitch for the MLP intermediate (whole 128-byte lines)
+    for _ in range(10):
+        ops.gemm_tn_ln(a, w, c2, stats, spec.hidden, spec.ln_eps, act=spec.act, out=o)
+    torch.cuda.synchronize(dev)
+    # best of three groups of ten launches — the burst peak it is divided by is itself a best-of-10 figure
+    # (MEASURED_PEAKS.json "how"); a single group right after the long timed loop sometimes catches a clock dip
+    n_k, groups = 10, []
     for _ in range(3):
-        ops.gemm_tn_ln(a, w, c2, stats, spec.hidden, spec.ln_eps, act=spec.act, out=o)
-    torch.cuda.synchronize(dev)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_k = 10
-    k0.record()
-    for _ in range(n_k):
-        ops.gemm_tn_ln(a, w, c2, stats, spec.hidden, spec.ln_eps, act=spec.act, out=o)
-    k1.record()
-    torch.cuda.synchronize(dev)
-    k_ms = k0.elapsed_time(k1) / n_k
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(n_k):
+            ops.gemm_tn_ln(a, w, c2, stats, spec.hidden, spec.ln_eps, act=spec.act, out=o)
+        k1.record()
+        torch.cuda.synchronize(dev)
+        groups.append(k0.elapsed_time(k1) / n_k)
+    k_ms = min(groups)
     k_tflops = 2.0 * M * spec.mlp * spec.hidden / (k_ms * 1e-3) / 1e12
     step_tflops = spec.flops_per_image() * B * args.steps / (total_ms * 1e-3) / 1e12  # per GPU
     traffic, traffic_src = None, None
@@ -307,6 +311,7 @@ def run_b200_arm(args):
         "frac": round(k_tflops / peaks["bf16_burst"], 4), "peak_source": peaks["source"] + " burst (kernel timed alone)",
         "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes": (M * spec.hidden + spec.mlp * spec.hidden + M * spec.mlp) * 2, "kernel_ms": round(k_ms, 4),
+        "kernel_ms_groups": [round(g, 4) for g in groups], "kernel_timing": "best of 3 groups of 10 launches, CUDA events",
         "step_achieved": round(step_tflops, 1), "step_peak_sustained": peaks["bf16_sustained"],
         "step_frac_sustained": round(step_tflops / peaks["bf16_sustained"], 4),
         "step_frac_burst": round(step_tflops / peaks["bf16_burst"], 4),
