@@ -111,3 +111,28 @@ def test_gpu_resize_extremes_and_properties(cuda_device):
     with pytest.raises(Exception, match="unsupported size"):
         ing([np.zeros((4, 16385, 3), np.uint8)])
     assert ing([]).shape == (0, 224, 224, 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_gpu_resize_random_sweep(cuda_device, seed):
+    """Random sizes between 1 and ~900 pixels per side, both resize modes, in ONE ragged batch per mode: up- and
+    down-scaling on either axis, identity on one axis, heavy aspect ratios (bounded so the oracle stays fast)."""
+    rng = np.random.default_rng(seed)
+    for mode, size in (("square", 224), ("shortest_crop", 336)):
+        imgs = []
+        for _ in range(24):
+            h = int(rng.choice([1, 2, 7, size - 1, size, size + 1, int(rng.integers(3, 900))]))
+            lim = (max(h // 4, 1), h * 4 + 4) if mode == "shortest_crop" else (1, 900)
+            w = int(np.clip(rng.choice([1, 3, size - 1, size, size + 1, int(rng.integers(3, 900))]), *lim))
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                im = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            elif kind == 1:  # saturated blocks: the bicubic lobes overshoot on both sides of every edge
+                im = (rng.integers(0, 2, (h, w, 3)) * 255).astype(np.uint8)
+            else:
+                im = np.full((h, w, 3), int(rng.integers(0, 256)), np.uint8)
+            imgs.append(im)
+        out = ingest.ImageIngest(MODES[mode], size, cuda_device)(imgs).cpu().numpy()
+        for k, im in enumerate(imgs):
+            np.testing.assert_array_equal(out[k], po.preprocess_u8(im, mode, size), err_msg=f"{mode} {im.shape}")
