@@ -75,7 +75,10 @@ enum { VLMFW_CDT_F16 = 0, VLMFW_CDT_BF16 = 1 };
 /* GEMM epilogues (kernel-level entry point, used by the parity tests) */
 enum {
     VLMFW_EPI_BIAS_BF16 = 0,     /* out_bf16 = act(acc + bias)                         */
-    VLMFW_EPI_BIAS_RESID_F32 = 1 /* out_f32  = acc + bias + resid_f32[row % resid_mod] */
+    VLMFW_EPI_BIAS_RESID_F32 = 1, /* out_f32  = acc + bias + resid_f32[row % resid_mod] */
+    VLMFW_EPI_BIAS_RESID_16 = 2   /* out_16   = round16(acc + bias + resid_16): the 16-bit residual stream, `resid` points to
+                                     16-bit data of the GEMM's dtype (ldr in elements), out may alias it; stats_out allowed
+                                     (sums of the ROUNDED values), h16_out not (the output is the 16-bit copy) */
 };
 
 typedef struct vlmfw_tower_cfg {

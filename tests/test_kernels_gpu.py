@@ -202,6 +202,28 @@ def test_gemm_residual_producer_stats_and_cast(cuda_device, m, n, k, form, block
     torch.testing.assert_close(tot[:, 1], (h * h).sum(1), rtol=1e-4, atol=2e-2)
 
 
+@pytest.mark.parametrize("m,n,k", [(384, 1152, 1152), (777, 1152, 4304), (130, 144, 304), (64, 1408, 6144),
+                                   (20000, 1024, 1024), (600, 1160, 320), (300, 1288, 192)])
+@pytest.mark.parametrize("form", ["1cta", "2cta"])
+@pytest.mark.parametrize("block_n", [0, 128, 192, 256])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_gemm_residual_16bit_stream(cuda_device, m, n, k, form, block_n, dtype):
+    """EPI_BIAS_RESID_16: h16 = round16(h16 + A W^T + bias) in place + row statistics of the rounded values."""
+    a = _rand((m, k), 40).to(dtype)
+    w = _rand((n, k), 41, 1 / math.sqrt(k)).to(dtype)
+    bias = _rand((n,), 42, 0.5)
+    h0 = (_rand((m, n), 43, 2.0) + 0.3).to(dtype)
+    h = h0.clone()
+    stats = ops.gemm_tn_resid16(a, w, bias, h, block_n=block_n | FORMS[form])
+    exact = h0.float() + a.float() @ w.float().t() + bias
+    ulp = 2.0 ** (-10 if dtype == torch.float16 else -7)  # one unit in the last place, relative
+    err = (h.float() - exact).abs()
+    assert (err <= 0.51 * ulp * exact.abs().clamp_min(2.0 ** -14) + 1e-4).all(), float(err.max())  # correctly rounded +- accumulation order
+    tot = stats.sum(dim=1)
+    torch.testing.assert_close(tot[:, 0], h.float().sum(1), rtol=1e-4, atol=2e-2)
+    torch.testing.assert_close(tot[:, 1], (h.float() ** 2).sum(1), rtol=1e-4, atol=2e-2)
+
+
 def test_gemm_folded_chain_matches_layernorm_linear(cuda_device):
     """producer -> consumer exactly as the tower chains them: h += a W_o^T + b_o; y = LN(h) W_1^T + b_1."""
     m, d, i = 3000, 1152, 4304

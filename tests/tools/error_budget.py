@@ -14,7 +14,7 @@ from vlmfw_b200 import specs, weights  # noqa: E402
 
 def run(spec, w, pv, q, dt):
     r = (lambda t: t.to(dt).float())
-    rq = {k: (r if k in q else (lambda t: t)) for k in ("w", "xn", "qkv", "p", "ctx", "mid", "patch")}
+    rq = {k: (r if k in q else (lambda t: t)) for k in ("w", "xn", "qkv", "p", "ctx", "mid", "patch", "h")}
     W = {k: (rq["w"](v) if v.dim() == 2 and k != "pos" else v) for k, v in w.items()}
     b = pv.shape[0]
     p, g, d = spec.patch_size, spec.image_size // spec.patch_size, spec.hidden
@@ -22,7 +22,7 @@ def run(spec, w, pv, q, dt):
     h = patches @ W["patch.w"].t() + (W["patch.b"] if spec.conv_bias else 0)
     if spec.has_cls:
         h = torch.cat([W["cls"].view(1, 1, d).expand(b, 1, d), h], 1)
-    h = h + W["pos"]
+    h = rq["h"](h + W["pos"])
     if spec.has_pre_ln:
         h = O._ln(h, W["pre_ln.w"], W["pre_ln.b"], spec.ln_eps)
     nh, dh = spec.heads, spec.head_dim
@@ -35,10 +35,10 @@ def run(spec, w, pv, q, dt):
         e = torch.exp(s - s.amax(-1, keepdim=True))
         ctx = (rq["p"](e) @ vv) / e.sum(-1, keepdim=True)
         ctx = rq["ctx"](ctx.transpose(1, 2).reshape(b, -1, d))
-        h = h + ctx @ W[L + "o.w"].t() + W[L + "o.b"]
+        h = rq["h"](h + ctx @ W[L + "o.w"].t() + W[L + "o.b"])  # "h": a 16-bit residual stream (not what the tower does)
         x = rq["xn"](O._ln(h, W[L + "ln2.w"], W[L + "ln2.b"], spec.ln_eps))
         m = rq["mid"](O._act(x @ W[L + "fc1.w"].t() + W[L + "fc1.b"], spec.act))
-        h = h + m @ W[L + "fc2.w"].t() + W[L + "fc2.b"]
+        h = rq["h"](h + m @ W[L + "fc2.w"].t() + W[L + "fc2.b"])
     return O.pool(spec, W, h, spec.pool)
 
 
@@ -53,7 +53,9 @@ def main():
         ref = run(spec, w, pv, set(), torch.float32)
         ref_l = torch.cat([O.head_forward(ref, hp) for hp in heads], 1)
         for dt in (torch.bfloat16, torch.float16):
-            for q in (["w"], ["xn"], ["qkv"], ["p"], ["ctx"], ["mid"], ["patch"], ["w", "xn", "qkv", "p", "ctx", "mid", "patch"],
+            only = os.environ.get("BUDGET_ONLY")
+            cases = [only.split("+")] if only else None
+            for q in cases or (["w"], ["xn"], ["qkv"], ["p"], ["ctx"], ["mid"], ["patch"], ["w", "xn", "qkv", "p", "ctx", "mid", "patch"],
                       ["w", "xn", "qkv", "ctx", "mid", "patch"]):
                 f = run(spec, w, pv, set(q), dt)
                 lg = torch.cat([O.head_forward(f, hp) for hp in heads], 1)

@@ -60,7 +60,9 @@ struct Cfg {
     // per-warp epilogue staging: generic 4 KB transpose buffer; 16-bit TMA-store path 2 x [32 x 64 B] boxes;
     // residual path RES_NBUF x [32 x RES_COLS fp32] boxes + the 16-bit cast box
     static constexpr int STG_PER_WARP =
-        GEN ? STAGING_PER_WARP : (EPI == VLMFW_EPI_BIAS_RESID_F32 ? RES_NBUF * RES_BOX_BYTES + H16_BOX_BYTES : 2 * 2048);
+        GEN ? STAGING_PER_WARP
+            : (EPI == VLMFW_EPI_BIAS_RESID_F32 ? RES_NBUF * RES_BOX_BYTES + H16_BOX_BYTES
+                                               : (EPI == VLMFW_EPI_BIAS_RESID_16 ? RES_NBUF * H16_BOX_BYTES : 2 * 2048));
     static constexpr int STAGING_BYTES = EPI_WARPS * STG_PER_WARP;
     static constexpr int BAR_BYTES = 512;
     static constexpr int RING_MAX = (SMEM_LIMIT - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
@@ -166,7 +168,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int s = 0; s < EPI_WARPS * RES_NBUF; ++s) mbar_init(&res_bar[s], 1);
         if constexpr (!GEN) {
             tma_prefetch_desc(&tmap_out);
-            if constexpr (EPI == VLMFW_EPI_BIAS_RESID_F32) tma_prefetch_desc(&tmap_res);
+            if constexpr (EPI != VLMFW_EPI_BIAS_BF16) tma_prefetch_desc(&tmap_res);
         }
         fence_mbar_init();
     }
@@ -370,6 +372,109 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         tma_store_2d(&tmap_out, stg_u32 + (q & 1u) * 2048u, nc, m0);
                         tma_store_commit();
                     }
+                }
+                release_acc();
+            }
+            if (lane == 0) tma_store_wait_all();
+        } else if constexpr (!GEN && EPI == VLMFW_EPI_BIAS_RESID_16) {
+            // ---- 16-bit residual stream, updated in place: out = round16(acc + bias + resid). ONE box type, [32 rows x 32
+            // cols] of 16-bit (64-byte rows, 64B-swizzled), ring of RES_NBUF per warp: TMA load, every thread updates its
+            // row in place, TMA store of the same box. The stored values are at once the residual stream and the next
+            // GEMM's A operand, and the row statistics are taken from the ROUNDED values, so the LayerNorm folded into
+            // that GEMM normalises exactly what it multiplies. Half the HBM and shared-memory bytes of the fp32 stream.
+            constexpr int RC = 32;
+            constexpr int RCHUNKS = COLS_PER_WARP / RC;
+            constexpr int BOX = H16_BOX_BYTES;
+            const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;  // SWIZZLE_64B
+            uint64_t* my_bar = res_bar + ew * RES_NBUF;
+            const int my_tiles = worker < num_tiles ? (num_tiles - worker + num_workers - 1) / num_workers : 0;
+            const uint32_t total_q = static_cast<uint32_t>(my_tiles) * RCHUNKS;
+            auto issue_load = [&](uint32_t qq) {  // lane 0 only
+                const int t = worker + static_cast<int>(qq / RCHUNKS) * num_workers;
+                const int c = static_cast<int>(qq % RCHUNKS);
+                const int cx = (t % n_tiles) * BN + half * COLS_PER_WARP + c * RC;
+                const int cy = (t / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
+                const uint32_t b = qq % RES_NBUF;
+                mbar_arrive_expect_tx(&my_bar[b], BOX);
+                tma_load_2d(stg + b * BOX, &tmap_res, &my_bar[b], cx, cy);
+            };
+            if (lane == 0 && !(p.dbg & 2)) {
+                for (uint32_t qq = 0; qq < RES_NBUF - 1 && qq < total_q; ++qq) issue_load(qq);
+            }
+            auto unpack2 = [&](uint32_t u, float& lo, float& hi) {
+                if (p.out_f16) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+                    lo = f.x;
+                    hi = f.y;
+                } else {
+                    lo = __uint_as_float(u << 16);
+                    hi = __uint_as_float(u & 0xFFFF0000u);
+                }
+            };
+            uint32_t q = 0;
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const int m0 = (tile / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
+                const int n0 = (tile % n_tiles) * BN + half * COLS_PER_WARP;
+                float s1 = 0.f, s2 = 0.f;
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < RCHUNKS; ++c, ++q) {
+                    if (p.dbg & 2) continue;
+                    const int nc = n0 + c * RC;
+                    uint32_t v[RC];
+                    tmem_ld_32x32(lane_taddr + static_cast<uint32_t>(acc * BN + c * RC), v);
+                    const uint32_t b = q % RES_NBUF;
+                    const uint32_t box = stg_u32 + b * BOX + static_cast<uint32_t>(lane) * 64u;
+                    mbar_wait(&my_bar[b], (q / RES_NBUF) & 1u);
+                    tmem_ld_wait();
+                    if (nc >= p.n) {  // warp-uniform: columns a narrow last tile never wrote must not reach the statistics
+#pragma unroll
+                        for (int j = 0; j < RC; ++j) v[j] = 0u;
+                    }
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) {  // 16 bytes = 8 columns
+                        float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (p.bias != nullptr && nc + 8 * static_cast<int>(j) < p.n) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 8 * j));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 8 * j + 4));
+                            bv[0] = b0.x, bv[1] = b0.y, bv[2] = b0.z, bv[3] = b0.w;
+                            bv[4] = b1.x, bv[5] = b1.y, bv[6] = b1.z, bv[7] = b1.w;
+                        }
+                        const uint32_t a = box + ((j ^ sw) << 4);
+                        uint32_t u[4];
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
+                                     : "r"(a));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float lo, hi;
+                            unpack2(u[i], lo, hi);
+                            lo += __uint_as_float(v[8 * j + 2 * i]) + bv[2 * i];
+                            hi += __uint_as_float(v[8 * j + 2 * i + 1]) + bv[2 * i + 1];
+                            u[i] = p.out_f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+                            unpack2(u[i], lo, hi);  // statistics of what is stored
+                            s1 += lo + hi;
+                            s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(u[0]), "r"(u[1]), "r"(u[2]),
+                                     "r"(u[3])
+                                     : "memory");
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_out, stg_u32 + b * BOX, nc, m0);
+                        tma_store_commit();
+                        // every bulk group but the newest has read its box: the box of chunk q - 1 takes the next load
+                        tma_store_wait_read<1>();
+                        if (q + RES_NBUF - 1 < total_q) issue_load(q + RES_NBUF - 1);
+                    }
+                    __syncwarp();
+                }
+                if (p.stats_out != nullptr && m0 + lane < p.m && !(p.dbg & 2)) {
+                    p.stats_out[static_cast<size_t>(m0 + lane) * p.stats_np + (tile % n_tiles) * 2 + half] =
+                        make_float2(s1, s2);
                 }
                 release_acc();
             }
@@ -713,6 +818,10 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
         } else {
             rc = get_tensor_map(g.out, g.m, g.n, g.ldo, 32, 32, dt16, 64, &tout);
             if (rc != VLMFW_OK) return rc;
+            if constexpr (EPI == VLMFW_EPI_BIAS_RESID_16) {
+                rc = get_tensor_map(g.resid, g.m, g.n, g.ldr, 32, 32, dt16, 64, &tres);
+                if (rc != VLMFW_OK) return rc;
+            }
         }
     }
     auto kern = gemm_bf16_tn_kernel<BN, EPI, ACT, CG, GEN>;
@@ -795,6 +904,10 @@ int dispatch_epi(const GemmArgs& g, cudaStream_t stream) {
     // the generic epilogue; everything else moves its output (and residual) with TMA
     const bool generic = g.grp > 0 || (g.resid_mod > 0 && (g.resid_mod % 32 != 0 || g.epi != VLMFW_EPI_BIAS_RESID_F32)) ||
                          (g.block_n & VLMFW_GEMM_FORCE_GENERIC_EPI);
+    if (g.epi == VLMFW_EPI_BIAS_RESID_16) {
+        VLMFW_REQUIRE(!generic, "gemm: the 16-bit residual epilogue has no row remap / broadcast residual");
+        return launch_one<BN, VLMFW_EPI_BIAS_RESID_16, VLMFW_ACT_NONE, CG, false>(g, stream);
+    }
     if (g.epi == VLMFW_EPI_BIAS_RESID_F32) {
         if (generic) return launch_one<BN, VLMFW_EPI_BIAS_RESID_F32, VLMFW_ACT_NONE, CG, true>(g, stream);
         return launch_one<BN, VLMFW_EPI_BIAS_RESID_F32, VLMFW_ACT_NONE, CG, false>(g, stream);
@@ -902,6 +1015,10 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     if (g.epi == VLMFW_EPI_BIAS_RESID_F32) {
         VLMFW_REQUIRE(g.resid != nullptr && g.ldr % 4 == 0 && g.ldr >= g.n, "gemm: residual epilogue needs resid/ldr");
         VLMFW_REQUIRE((reinterpret_cast<uintptr_t>(g.resid) & 15) == 0, "gemm: resid must be 16-byte aligned");
+    } else if (g.epi == VLMFW_EPI_BIAS_RESID_16) {
+        VLMFW_REQUIRE(g.resid != nullptr && g.ldr % 8 == 0 && g.ldr >= g.n, "gemm: 16-bit residual epilogue needs resid/ldr");
+        VLMFW_REQUIRE((reinterpret_cast<uintptr_t>(g.resid) & 15) == 0, "gemm: resid must be 16-byte aligned");
+        VLMFW_REQUIRE(g.h16_out == nullptr && g.act == VLMFW_ACT_NONE, "gemm: 16-bit residual epilogue has no h16_out / activation");
     } else {
         VLMFW_REQUIRE(g.epi == VLMFW_EPI_BIAS_BF16, "gemm: unknown epilogue %d", g.epi);
     }
@@ -914,8 +1031,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
         VLMFW_REQUIRE((reinterpret_cast<uintptr_t>(g.ln_stats) & 7) == 0, "gemm: ln_stats must be 8-byte aligned");
     }
     if (g.stats_out != nullptr || g.h16_out != nullptr) {
-        VLMFW_REQUIRE(g.epi == VLMFW_EPI_BIAS_RESID_F32 && !generic_epi,
-                      "gemm: row statistics / 16-bit copy are produced by the TMA residual epilogue only");
+        VLMFW_REQUIRE((g.epi == VLMFW_EPI_BIAS_RESID_F32 || g.epi == VLMFW_EPI_BIAS_RESID_16) && !generic_epi,
+                      "gemm: row statistics / 16-bit copy are produced by the TMA residual epilogues only");
         if (g.h16_out != nullptr)
             VLMFW_REQUIRE(g.ld_h16 >= g.n && g.ld_h16 % 8 == 0 && (reinterpret_cast<uintptr_t>(g.h16_out) & 15) == 0,
                           "gemm: h16_out needs ld_h16 >= n, a multiple of 8, and 16-byte alignment");

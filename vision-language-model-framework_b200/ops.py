@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from .specs import ACT_NONE
 
-EPI_BIAS_BF16, EPI_BIAS_RESID_F32 = 0, 1
+EPI_BIAS_BF16, EPI_BIAS_RESID_F32, EPI_BIAS_RESID_16 = 0, 1, 2
 
 
 def _st(t: torch.Tensor) -> int:
@@ -160,6 +160,26 @@ def gemm_tn_resid_stats(a16: torch.Tensor, w16: torch.Tensor, bias: Optional[tor
     with torch.cuda.device(a16.device):
         _lib.check(_lib.load().vlmfw_gemm_tn_ex(C.byref(d), _st(a16)))
     return h16, stats
+
+
+def gemm_tn_resid16(a16: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tensor], h16: torch.Tensor, *,
+                    block_n: int = 0) -> torch.Tensor:
+    """16-bit residual stream: ``h16 = round16(h16 + a16 @ w16^T + bias)`` in place; returns the row statistics
+    ``[M, parts, 2]`` (sum, sum of squares of the ROUNDED values per column slice) for the LayerNorm folded into the next GEMM."""
+    _need(a16, a16.dtype, "a16")
+    _need(w16, a16.dtype, "w16")
+    _need(h16, a16.dtype, "h16")
+    m, k = a16.shape
+    n = w16.shape[0]
+    parts = gemm_stats_parts(n, block_n)
+    stats = torch.full((m, parts, 2), float("nan"), dtype=torch.float32, device=a16.device)
+    d = _lib.GemmDesc(a=a16.data_ptr(), lda=a16.stride(0), w=w16.data_ptr(), ldw=w16.stride(0), dtype=_dt(a16, "a16"),
+                      m=m, n=n, k=k, bias=None if bias is None else bias.data_ptr(), epi=EPI_BIAS_RESID_16, act=ACT_NONE,
+                      out=h16.data_ptr(), ldo=h16.stride(0), resid=h16.data_ptr(), ldr=h16.stride(0), block_n=block_n,
+                      ln_stats=None, ln_np=0, ln_dim=0, ln_eps=0.0, h16_out=None, ld_h16=0, stats_out=stats.data_ptr())
+    with torch.cuda.device(a16.device):
+        _lib.check(_lib.load().vlmfw_gemm_tn_ex(C.byref(d), _st(a16)))
+    return stats
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
