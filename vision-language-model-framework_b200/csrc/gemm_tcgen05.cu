@@ -428,9 +428,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t box = stg_u32 + b * BOX + static_cast<uint32_t>(lane) * 64u;
                     mbar_wait(&my_bar[b], (q / RES_NBUF) & 1u);
                     tmem_ld_wait();
-                    if (nc >= p.n) {  // warp-uniform: columns a narrow last tile never wrote must not reach the statistics
+                    // warp-uniform: columns a narrow last tile never wrote (its MMA is as wide as N rounded up to 16) hold
+                    // stale TMEM and must not reach the statistics
+                    const int n16 = (p.n + 15) & ~15;
 #pragma unroll
-                        for (int j = 0; j < RC; ++j) v[j] = 0u;
+                    for (int g16 = 0; g16 < RC / 16; ++g16) {
+                        if (nc + 16 * g16 >= n16) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[16 * g16 + j] = 0u;
+                        }
                     }
 #pragma unroll
                     for (uint32_t j = 0; j < 4; ++j) {  // 16 bytes = 8 columns
