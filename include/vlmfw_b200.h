@@ -143,6 +143,10 @@ int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t pix_fmt, int
                         size_t workspace_bytes, float* pooled_out, void* stream);
 /* same, but also exposes the final hidden state [B*S, D] fp32 inside the workspace (for parity tests) */
 const float* vlmfw_tower_hidden_ptr(const vlmfw_tower* t, void* workspace);
+/* fp16 towers keep the residual stream in fp16 (the final hidden state then lives in the 16-bit buffer this returns, [B*S, D]
+ * of the tower's compute dtype); NULL when the tower keeps the fp32 stream (bf16 towers, VLMFW_RESIDUAL=32), in which case
+ * vlmfw_tower_hidden_ptr is the final hidden state. */
+const void* vlmfw_tower_hidden16_ptr(const vlmfw_tower* t, void* workspace, int32_t batch);
 /* number of kernels the last forward launched (bench.py's gpu_launches claim) */
 int64_t vlmfw_tower_last_launches(const vlmfw_tower* t);
 /* Host-buffer convenience for non-torch hosts: H2D copy, forward, D2H copy, synchronous.

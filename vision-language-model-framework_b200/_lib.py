@@ -70,6 +70,7 @@ SIGNATURES = {
     "vlmfw_tower_tokens": (_i32, [_vp]),
     "vlmfw_tower_forward": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp]),
     "vlmfw_tower_hidden_ptr": (_vp, [_vp, _vp]),
+    "vlmfw_tower_hidden16_ptr": (_vp, [_vp, _vp, _i32]),
     "vlmfw_tower_last_launches": (_i64, [_vp]),
     "vlmfw_tower_forward_host": (C.c_int, [_vp, _vp, _i32, _vp]),
     "vlmfw_preproc_create": (C.c_int, [_i32, _i32, C.POINTER(_vp)]),

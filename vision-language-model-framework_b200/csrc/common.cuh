@@ -100,6 +100,9 @@ int launch_im2col(const void* pixels, int pix_fmt, int batch, int image_size, in
 int launch_fill_cls(const float* cls_pos0, float* h, int batch, int tokens, int dim, cudaStream_t stream);
 int launch_pool(const float* h, int batch, int tokens, int dim, int pool, const float* gamma, const float* beta,
                 float eps, float* pooled, cudaStream_t stream);
+// same, reading a 16-bit (VLMFW_DT_F16 / VLMFW_DT_BF16) or fp32 hidden state
+int launch_pool_dt(const void* h, int in_dt, int batch, int tokens, int dim, int pool, const float* gamma,
+                   const float* beta, float eps, float* pooled, cudaStream_t stream);
 int launch_pack_16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, bool f16, cudaStream_t stream);
 // max |x| over a device fp32 array, returned to the host (synchronises `stream`; load-time only)
 int device_absmax(const float* src, int64_t numel, float* host_out, cudaStream_t stream);

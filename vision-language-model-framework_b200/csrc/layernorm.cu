@@ -71,29 +71,65 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
+// Input element type of the pooling kernels: the fp32 residual stream, or the 16-bit one (fp16 / bf16 towers that keep the
+// stream in the tensor-core format). ld4: elements [4c, 4c + 4) of a row; ld1: one element.
+template <int DT>
+__device__ __forceinline__ float4 ld4(const void* row, int c) {
+    if constexpr (DT == VLMFW_DT_F32) {
+        return reinterpret_cast<const float4*>(row)[c];
+    } else {
+        const uint2 u = reinterpret_cast<const uint2*>(row)[c];
+        float4 f;
+        if constexpr (DT == VLMFW_DT_F16) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+            f = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+            f = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                            __uint_as_float(u.y & 0xFFFF0000u));
+        }
+        return f;
+    }
+}
+template <int DT>
+__device__ __forceinline__ float ld1(const void* base, size_t i) {
+    if constexpr (DT == VLMFW_DT_F32) {
+        return static_cast<const float*>(base)[i];
+    } else if constexpr (DT == VLMFW_DT_F16) {
+        return __half2float(static_cast<const __half*>(base)[i]);
+    } else {
+        return __uint_as_float(static_cast<uint32_t>(static_cast<const uint16_t*>(base)[i]) << 16);
+    }
+}
+template <int DT>
+__device__ __forceinline__ const void* row_ptr(const void* base, size_t elems) {
+    return static_cast<const uint8_t*>(base) + elems * (DT == VLMFW_DT_F32 ? 4 : 2);
+}
+
 // SigLIP: pooled[b, d] = mean_s ( (h[b,s,d] - mu_s) * rstd_s ) * gamma[d] + beta[d].
 // One CTA (1024 threads) per image. Phase 1: warps compute per-token (mu, rstd) into smem. Phase 2: thread d accumulates
 // its column over the tokens — the image's 1.2 MB was just read by phase 1, so this second pass is served by L2 and
 // HBM sees each row once (the first version used one CTA per 256-column slab, each recomputing every token's
 // statistics: 4x the algorithmic DRAM reads in the round-1 ncu capture).
-__global__ void __launch_bounds__(1024) pool_ln_mean_kernel(const float* __restrict__ h, int tokens, int dim,
+template <int DT>
+__global__ void __launch_bounds__(1024) pool_ln_mean_kernel(const void* __restrict__ h, int tokens, int dim,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps,
                                                             float* __restrict__ pooled) {
     extern __shared__ float2 stats[];  // [tokens] (mean, rstd)
     const int b = blockIdx.x;
-    const float* hb = h + static_cast<size_t>(b) * tokens * dim;
+    const void* hb = row_ptr<DT>(h, static_cast<size_t>(b) * tokens * dim);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int nchunks = dim >> 2;
     for (int s = warp; s < tokens; s += nwarps) {
-        const float4* xr = reinterpret_cast<const float4*>(hb + static_cast<size_t>(s) * dim);
+        const void* xr = row_ptr<DT>(hb, static_cast<size_t>(s) * dim);
         float4 v[LN_MAX_CHUNKS];
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
             const int c = i * 32 + lane;
             if (c < nchunks) {
-                v[i] = xr[c];
+                v[i] = ld4<DT>(xr, c);
                 sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
             }
         }
@@ -116,14 +152,14 @@ __global__ void __launch_bounds__(1024) pool_ln_mean_kernel(const float* __restr
         int s = 0;
         for (; s + 4 <= tokens; s += 4) {
             const float2 t0 = stats[s], t1 = stats[s + 1], t2 = stats[s + 2], t3 = stats[s + 3];
-            acc0 += (hb[static_cast<size_t>(s) * dim + d] - t0.x) * t0.y;
-            acc1 += (hb[static_cast<size_t>(s + 1) * dim + d] - t1.x) * t1.y;
-            acc2 += (hb[static_cast<size_t>(s + 2) * dim + d] - t2.x) * t2.y;
-            acc3 += (hb[static_cast<size_t>(s + 3) * dim + d] - t3.x) * t3.y;
+            acc0 += (ld1<DT>(hb, static_cast<size_t>(s) * dim + d) - t0.x) * t0.y;
+            acc1 += (ld1<DT>(hb, static_cast<size_t>(s + 1) * dim + d) - t1.x) * t1.y;
+            acc2 += (ld1<DT>(hb, static_cast<size_t>(s + 2) * dim + d) - t2.x) * t2.y;
+            acc3 += (ld1<DT>(hb, static_cast<size_t>(s + 3) * dim + d) - t3.x) * t3.y;
         }
         for (; s < tokens; ++s) {
             const float2 st = stats[s];
-            acc0 += (hb[static_cast<size_t>(s) * dim + d] - st.x) * st.y;
+            acc0 += (ld1<DT>(hb, static_cast<size_t>(s) * dim + d) - st.x) * st.y;
         }
         const float acc = (acc0 + acc1) + (acc2 + acc3);
         pooled[static_cast<size_t>(b) * dim + d] = acc / static_cast<float>(tokens) * gamma[d] + beta[d];
@@ -131,19 +167,21 @@ __global__ void __launch_bounds__(1024) pool_ln_mean_kernel(const float* __restr
 }
 
 // CLIP adapter: mean over all tokens (first = 0, count = tokens) or the CLS row (count = 1) of the raw hidden state.
-__global__ void __launch_bounds__(256) pool_mean_kernel(const float* __restrict__ h, int tokens, int dim, int count,
+template <int DT>
+__global__ void __launch_bounds__(256) pool_mean_kernel(const void* __restrict__ h, int tokens, int dim, int count,
                                                         float* __restrict__ pooled) {
     const int b = blockIdx.x;
     const int d = blockIdx.y * blockDim.x + threadIdx.x;
     if (d >= dim) return;
-    const float* hb = h + static_cast<size_t>(b) * tokens * dim;
+    const void* hb = row_ptr<DT>(h, static_cast<size_t>(b) * tokens * dim);
     float acc = 0.f;
-    for (int s = 0; s < count; ++s) acc += hb[static_cast<size_t>(s) * dim + d];
+    for (int s = 0; s < count; ++s) acc += ld1<DT>(hb, static_cast<size_t>(s) * dim + d);
     pooled[static_cast<size_t>(b) * dim + d] = acc / static_cast<float>(count);
 }
 
 // BLIP-2: y = LN(h[b,0,:]); pooled = LN(y) with the same gamma/beta. One warp per image.
-__global__ void __launch_bounds__(128) pool_cls_ln2_kernel(const float* __restrict__ h, int batch, int tokens, int dim,
+template <int DT>
+__global__ void __launch_bounds__(128) pool_cls_ln2_kernel(const void* __restrict__ h, int batch, int tokens, int dim,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps,
                                                            float* __restrict__ pooled) {
@@ -151,14 +189,14 @@ __global__ void __launch_bounds__(128) pool_cls_ln2_kernel(const float* __restri
     const int lane = threadIdx.x & 31;
     if (b >= batch) return;
     const int nchunks = dim >> 2;
-    const float4* xr = reinterpret_cast<const float4*>(h + static_cast<size_t>(b) * tokens * dim);
+    const void* xr = row_ptr<DT>(h, static_cast<size_t>(b) * tokens * dim);
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
     float4 v[LN_MAX_CHUNKS];
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
         const int c = i * 32 + lane;
-        if (c < nchunks) v[i] = xr[c];
+        if (c < nchunks) v[i] = ld4<DT>(xr, c);
     }
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
@@ -337,30 +375,26 @@ int launch_layernorm(const float* x, int rows, int dim, const float* gamma, cons
     return VLMFW_OK;
 }
 
-int launch_pool(const float* h, int batch, int tokens, int dim, int pool, const float* gamma, const float* beta,
-                float eps, float* pooled, cudaStream_t stream) {
-    VLMFW_REQUIRE(h && pooled, "pool: null pointer");
-    VLMFW_REQUIRE(batch > 0 && tokens > 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAX_CHUNKS * 128,
-                  "pool: bad shape batch=%d tokens=%d dim=%d", batch, tokens, dim);
-    int rc = device_check();
-    if (rc != VLMFW_OK) return rc;
+template <int DT>
+static int launch_pool_t(const void* h, int batch, int tokens, int dim, int pool, const float* gamma, const float* beta,
+                         float eps, float* pooled, cudaStream_t stream) {
     const int threads = 256;
     dim3 grid(batch, (dim + threads - 1) / threads);
     switch (pool) {
         case VLMFW_POOL_LN_MEAN:
             VLMFW_REQUIRE(gamma && beta, "pool: LN_MEAN needs gamma/beta");
             VLMFW_REQUIRE(tokens * sizeof(float2) <= 48 * 1024, "pool: too many tokens %d", tokens);
-            pool_ln_mean_kernel<<<batch, 1024, tokens * sizeof(float2), stream>>>(h, tokens, dim, gamma, beta, eps, pooled);
+            pool_ln_mean_kernel<DT><<<batch, 1024, tokens * sizeof(float2), stream>>>(h, tokens, dim, gamma, beta, eps, pooled);
             break;
         case VLMFW_POOL_MEAN:
-            pool_mean_kernel<<<grid, threads, 0, stream>>>(h, tokens, dim, tokens, pooled);
+            pool_mean_kernel<DT><<<grid, threads, 0, stream>>>(h, tokens, dim, tokens, pooled);
             break;
         case VLMFW_POOL_CLS:
-            pool_mean_kernel<<<grid, threads, 0, stream>>>(h, tokens, dim, 1, pooled);
+            pool_mean_kernel<DT><<<grid, threads, 0, stream>>>(h, tokens, dim, 1, pooled);
             break;
         case VLMFW_POOL_LN_CLS_LN:
             VLMFW_REQUIRE(gamma && beta, "pool: LN_CLS_LN needs gamma/beta");
-            pool_cls_ln2_kernel<<<(batch + 3) / 4, 128, 0, stream>>>(h, batch, tokens, dim, gamma, beta, eps, pooled);
+            pool_cls_ln2_kernel<DT><<<(batch + 3) / 4, 128, 0, stream>>>(h, batch, tokens, dim, gamma, beta, eps, pooled);
             break;
         default:
             set_error("pool: unknown mode %d", pool);
@@ -368,6 +402,23 @@ int launch_pool(const float* h, int batch, int tokens, int dim, int pool, const 
     }
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
+}
+
+int launch_pool_dt(const void* h, int in_dt, int batch, int tokens, int dim, int pool, const float* gamma,
+                   const float* beta, float eps, float* pooled, cudaStream_t stream) {
+    VLMFW_REQUIRE(h && pooled, "pool: null pointer");
+    VLMFW_REQUIRE(batch > 0 && tokens > 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAX_CHUNKS * 128,
+                  "pool: bad shape batch=%d tokens=%d dim=%d", batch, tokens, dim);
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    if (in_dt == VLMFW_DT_F16) return launch_pool_t<VLMFW_DT_F16>(h, batch, tokens, dim, pool, gamma, beta, eps, pooled, stream);
+    if (in_dt == VLMFW_DT_BF16) return launch_pool_t<VLMFW_DT_BF16>(h, batch, tokens, dim, pool, gamma, beta, eps, pooled, stream);
+    return launch_pool_t<VLMFW_DT_F32>(h, batch, tokens, dim, pool, gamma, beta, eps, pooled, stream);
+}
+
+int launch_pool(const float* h, int batch, int tokens, int dim, int pool, const float* gamma, const float* beta,
+                float eps, float* pooled, cudaStream_t stream) {
+    return launch_pool_dt(h, VLMFW_DT_F32, batch, tokens, dim, pool, gamma, beta, eps, pooled, stream);
 }
 
 }  // namespace vlmfw

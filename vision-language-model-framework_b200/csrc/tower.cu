@@ -116,6 +116,10 @@ struct vlmfw_tower {
     std::vector<LayerW> layers;
     void* patch_w = nullptr;  // 16-bit [D, kpad]
     bool f16 = true;  // cfg.compute_dtype == VLMFW_CDT_F16
+    // fp16 towers keep the residual stream itself in fp16 (xn is the stream): half the HBM traffic of the
+    // out-proj / fc2 epilogues, which put out-proj on the HBM roofline with an fp32 stream. bf16 towers (8-bit mantissa)
+    // and VLMFW_RESIDUAL=32 keep the fp32 stream.
+    bool resid16 = false;
     float* patch_b = nullptr;
     float* cls = nullptr;
     float* pos = nullptr;  // [S, D]
@@ -193,6 +197,10 @@ extern "C" int vlmfw_tower_create(const vlmfw_tower_cfg* cfg, vlmfw_tower** out)
     vlmfw_tower* t = new vlmfw_tower();
     t->cfg = *cfg;
     t->f16 = cfg->compute_dtype == VLMFW_CDT_F16;
+    {
+        const char* e = getenv("VLMFW_RESIDUAL");
+        t->resid16 = t->f16 && !(e != nullptr && atoi(e) == 32);
+    }
     const int g = cfg->image_size / cfg->patch_size;
     t->P = g * g;
     t->S = t->P + (cfg->has_cls ? 1 : 0);
@@ -316,6 +324,10 @@ extern "C" const float* vlmfw_tower_hidden_ptr(const vlmfw_tower* t, void* works
     return static_cast<const float*>(workspace);
 }
 extern "C" int64_t vlmfw_tower_last_launches(const vlmfw_tower* t) { return t ? t->last_launches : 0; }
+extern "C" const void* vlmfw_tower_hidden16_ptr(const vlmfw_tower* t, void* workspace, int32_t batch) {
+    if (!t || !workspace || batch <= 0 || !t->resid16) return nullptr;
+    return static_cast<const uint8_t*>(workspace) + t->off_xn(batch);
+}
 
 static int build_derived(vlmfw_tower* t, cudaStream_t st) {
     if (t->derived_ok) return VLMFW_OK;
@@ -453,13 +465,19 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.n = D;
         g.k = D;
         g.bias = w.bo;
-        g.epi = VLMFW_EPI_BIAS_RESID_F32;
-        g.out = h;
+        if (t->resid16) {  // xn IS the residual stream: updated in place, statistics of the rounded rows
+            g.epi = VLMFW_EPI_BIAS_RESID_16;
+            g.out = xn;
+            g.resid = static_cast<const float*>(xn);
+        } else {
+            g.epi = VLMFW_EPI_BIAS_RESID_F32;
+            g.out = h;
+            g.resid = h;
+            g.h16_out = xn;
+            g.ld_h16 = D;
+        }
         g.ldo = D;
-        g.resid = h;
         g.ldr = D;
-        g.h16_out = xn;
-        g.ld_h16 = D;
         g.stats_out = stats;
         rc = launch_gemm(g, st);
         if (rc != VLMFW_OK) return rc;
@@ -493,21 +511,32 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.n = D;
         g.k = I;
         g.bias = w.b2;
-        g.epi = VLMFW_EPI_BIAS_RESID_F32;
-        g.out = h;
         g.ldo = D;
-        g.resid = h;
         g.ldr = D;
-        if (li + 1 < t->L) {  // the last layer feeds the pooling kernel, which reads the fp32 rows
-            g.h16_out = xn;
-            g.ld_h16 = D;
-            g.stats_out = stats;
+        if (t->resid16) {
+            g.epi = VLMFW_EPI_BIAS_RESID_16;
+            g.out = xn;
+            g.resid = static_cast<const float*>(xn);
+            if (li + 1 < t->L) g.stats_out = stats;
+        } else {
+            g.epi = VLMFW_EPI_BIAS_RESID_F32;
+            g.out = h;
+            g.resid = h;
+            if (li + 1 < t->L) {  // the last layer feeds the pooling kernel, which reads the fp32 rows
+                g.h16_out = xn;
+                g.ld_h16 = D;
+                g.stats_out = stats;
+            }
         }
         rc = launch_gemm(g, st);
         if (rc != VLMFW_OK) return rc;
     }
     // ---- adapter pooling -> [B, D] fp32
-    rc = launch_pool(h, batch, S, D, t->cfg.pool, t->post_w, t->post_b, t->cfg.ln_eps, pooled_out, st);
+    if (t->resid16)
+        rc = launch_pool_dt(xn, t->f16 ? VLMFW_DT_F16 : VLMFW_DT_BF16, batch, S, D, t->cfg.pool, t->post_w, t->post_b,
+                            t->cfg.ln_eps, pooled_out, st);
+    else
+        rc = launch_pool(h, batch, S, D, t->cfg.pool, t->post_w, t->post_b, t->cfg.ln_eps, pooled_out, st);
     if (rc != VLMFW_OK) return rc;
     t->last_launches = launch_counter() - launches0;
     return VLMFW_OK;

@@ -161,6 +161,11 @@ class TowerEngine:
         """Final residual stream [B, S, D] fp32 of the most recent forward (a view into the workspace)."""
         ws = self._workspace(batch)
         n = batch * self.spec.tokens * self.spec.hidden
+        p16 = self._lib.vlmfw_tower_hidden16_ptr(self._h, ws.data_ptr(), batch)
+        if p16:  # fp16 towers: the residual stream is the 16-bit buffer itself
+            off = int(p16) - ws.data_ptr()
+            dt = torch.float16 if self.compute_dtype == "f16" else torch.bfloat16
+            return ws[off: off + n * 2].view(dt).view(batch, self.spec.tokens, self.spec.hidden)
         return ws[: n * 4].view(torch.float32).view(batch, self.spec.tokens, self.spec.hidden)
 
     @property
