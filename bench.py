@@ -328,8 +328,10 @@ def run_b200_arm(args):
             "data": "synthetic",
             "config": {"workload": WORKLOADS[args.model] + f", batch {B}/GPU",
                        "numerics": f"{eng.compute_dtype} tensor-core operands (tcgen05 kind::f16: same pipe and peak for "
-                                   "fp16 and bf16), fp32 accumulation in TMEM, fp32 residual stream / LayerNorm / softmax "
-                                   "/ pooling / probe",
+                                   "fp16 and bf16), fp32 accumulation in TMEM, "
+                                   + ("fp16 residual stream (VLMFW_RESIDUAL=32: fp32)" if eng.compute_dtype == "f16"
+                                      and os.environ.get("VLMFW_RESIDUAL") != "32" else "fp32 residual stream")
+                                   + ", fp32 LayerNorm statistics / softmax / pooling / probe",
                        "global_batch": B * env.world, "parallelism": f"dp{env.world}",
                        "l2": "no flush needed: per-step activation working set (~1.9 GB) >> 126 MB L2",
                        "cuda_graph": use_graph},

@@ -67,9 +67,11 @@ enum { VLMFW_DT_BF16 = 0, VLMFW_DT_F16 = 1, VLMFW_DT_F32 = 2 };
  *   F16  (default): 11-bit mantissa. Weight rounding is the dominant error term of this path because it is coherent
  *         across tokens and survives mean pooling (DESIGN.md "numerics": bf16 weights alone put the probe-logit error at
  *         1.5e-2, above the 1e-2 tolerance; fp16 gives 1.2e-3). It is also what the reference itself runs on a GPU
- *         (fp16 autocast, probing/test/base_tester.py:50). The residual stream, LayerNorm statistics, softmax and all
- *         accumulation stay fp32; 16-bit stores saturate to +-65504 instead of overflowing to inf.
- *   BF16: 8-bit mantissa, fp32 range — for checkpoints whose weights exceed the fp16 range (set_weight reports
+ *         (fp16 autocast, probing/test/base_tester.py:50). LayerNorm statistics, softmax and all accumulation stay fp32;
+ *         the residual stream itself is kept in fp16 (it is at once the next GEMM's A operand; measured cost 3e-4 of
+ *         logit error, gain 4.6 % of the step — VLMFW_RESIDUAL=32 in the environment keeps an fp32 stream);
+ *         16-bit stores saturate to +-65504 instead of overflowing to inf.
+ *   BF16: 8-bit mantissa, fp32 range, fp32 residual stream — for checkpoints whose weights exceed the fp16 range (set_weight reports
  *         VLMFW_E_RANGE and the host recreates the tower with this mode). */
 enum { VLMFW_CDT_F16 = 0, VLMFW_CDT_BF16 = 1 };
 /* GEMM epilogues (kernel-level entry point, used by the parity tests) */

@@ -51,6 +51,30 @@ def test_bf16_compute_mode(cuda_device, name):
     assert torch.nn.functional.cosine_similarity(got, ref, dim=1).min() >= COS_MIN
 
 
+@pytest.mark.parametrize("name", ["siglip_tiny", "clip_tiny", "eva_tiny", "siglip_so400m"])
+def test_fp32_residual_stream_mode(cuda_device, monkeypatch, name):
+    """fp16 towers keep the residual stream in fp16 by default; VLMFW_RESIDUAL=32 (read when the tower is created) keeps
+    it in fp32. Both must meet the tolerance, and they must differ (i.e. the switch really switches)."""
+    spec = specs.SPECS[name]
+    sd = weights.seeded_hf_state_dict(spec, 5)
+    imgs = weights.seeded_images_u8(3, spec.image_size, 8, smooth=True)
+    outs = {}
+    for mode in ("16", "32"):
+        monkeypatch.setenv("VLMFW_RESIDUAL", mode)
+        eng = TowerEngine(spec, "cuda:0")
+        eng.load_hf_state_dict(sd)
+        outs[mode] = eng.forward(imgs.cuda()).cpu()
+        assert eng.hidden_state(3).dtype == (torch.float16 if mode == "16" else torch.float32)
+        eng.close()
+    pv = O.preprocess_u8(imgs, spec.pix_mean, spec.pix_std)
+    ref = O.tower_features(spec, weights.hf_to_canonical(spec, sd), pv) if spec.layers <= 4 else None
+    if ref is not None:
+        for mode in outs:
+            assert torch.nn.functional.cosine_similarity(outs[mode], ref).min() >= COS_MIN
+    assert torch.nn.functional.cosine_similarity(outs["16"], outs["32"]).min() >= 0.99999
+    assert not torch.equal(outs["16"], outs["32"])
+
+
 def test_fp16_range_overflow_falls_back_to_bf16(cuda_device):
     """A checkpoint with a weight beyond +-65504 cannot be stored in fp16: set_weight reports VLMFW_E_RANGE and the
     engine rebuilds the tower with bf16 operands instead of silently producing inf."""
