@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--only", default="")
     ap.add_argument("--no-cublas", action="store_true")
+    ap.add_argument("--resid32", action="store_true", help="fp32 residual epilogue (bf16 towers / VLMFW_RESIDUAL=32)")
     ap.add_argument("--dense-ld", action="store_true", help="row pitch = row length (the tower pads 16-bit rows to 128 B)")
     args = ap.parse_args()
     m = args.m
@@ -52,7 +53,11 @@ def main():
         w.copy_(torch.randn(n, k, device=dev) / math.sqrt(k))
         bias = torch.randn(n, device=dev)
         flops = 2.0 * m * n * k
-        if kind == "resid":
+        if kind == "resid" and not args.resid32:
+            # what the fp16 tower runs: the 16-bit residual stream updated in place (+ row statistics)
+            h16 = (torch.randn(m, n, device=dev)).to(DT)
+            fn = lambda: ops.gemm_tn_resid16(a, w, bias, h16, block_n=args.block_n)  # noqa: E731
+        elif kind == "resid":
             h = torch.randn(m, n, device=dev)
             fn = lambda: ops.gemm_tn(a, w, bias, resid=h, out=h, block_n=args.block_n)  # noqa: E731
         else:

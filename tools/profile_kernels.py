@@ -39,10 +39,10 @@ for it in range(2):  # the tower's launch sequence for one layer (tower.cu), at 
     xn, stats = ops.row_stats_cast(h, dtype=DT, parts=parts)
     qkv = ops.gemm_tn_ln(xn, wqf, bqc, stats, D, 1e-6)
     ctx = ops.attention(qkv, B, spec.tokens, spec.heads, spec.head_dim)
-    xn, stats = ops.gemm_tn_resid_stats(ctx, wo, bo, h)
+    stats = ops.gemm_tn_resid16(ctx, wo, bo, xn)  # the fp16 tower's residual stream: xn updated in place
     ops.gemm_tn_ln(xn, w1f, b1c, stats, D, 1e-6, act=spec.act, out=mid)
-    xn, stats = ops.gemm_tn_resid_stats(mid, w2, b2, h)
-    pooled = ops.pool(h.view(B, spec.tokens, D), specs.POOL_LN_MEAN, gamma, beta, 1e-6)
+    stats = ops.gemm_tn_resid16(mid, w2, b2, xn)
+    pooled = ops.pool(xn.float().view(B, spec.tokens, D), specs.POOL_LN_MEAN, gamma, beta, 1e-6)
     if os.environ.get("VLMFW_PROFILE_CUBLAS") == "1":  # the library GEMM on the fc1 shape, for a side-by-side ncu read
         torch.matmul(xn, w1.t())
     torch.cuda.synchronize()
