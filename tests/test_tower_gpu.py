@@ -75,6 +75,37 @@ def test_fp32_residual_stream_mode(cuda_device, monkeypatch, name):
     assert not torch.equal(outs["16"], outs["32"])
 
 
+@pytest.mark.parametrize("name", ["siglip_tiny", "clip_tiny", "eva_tiny"])
+@pytest.mark.parametrize("residual", ["16", "32"])
+def test_massive_activation_channels(cuda_device, monkeypatch, name, residual):
+    """Real ViT checkpoints carry a few residual-stream channels hundreds of times larger than the rest. The fp16 stream
+    must hold them (range 65504, relative precision 2^-11 at any magnitude): a position embedding with three channels at
+    +-300 (the stream keeps them through every layer) against the fp32 oracle, both stream modes."""
+    spec = specs.SPECS[name]
+    sd = weights.seeded_hf_state_dict(spec, 4)
+    key = next(k for k in sd if k.endswith("position_embedding.weight") or k.endswith("position_embedding"))
+    pos = sd[key].clone()
+    pos[..., 0] += 300.0
+    pos[..., 5] -= 300.0
+    pos[..., spec.hidden - 1] += 150.0
+    sd[key] = pos
+    monkeypatch.setenv("VLMFW_RESIDUAL", residual)
+    eng = TowerEngine(spec, "cuda:0")
+    eng.load_hf_state_dict(sd)
+    imgs = weights.seeded_images_u8(4, spec.image_size, 9, smooth=True)
+    got = eng.forward(imgs.cuda()).cpu()
+    hid = eng.hidden_state(4).float().cpu()
+    pv = O.preprocess_u8(imgs, spec.pix_mean, spec.pix_std)
+    can = weights.hf_to_canonical(spec, sd)
+    ref = O.tower_features(spec, can, pv)
+    ref_hid = O.last_hidden(spec, {k: v.float() for k, v in can.items()}, pv)
+    assert ref_hid.abs().max() > 100  # the outlier channels really are in the stream
+    assert torch.isfinite(got).all()
+    assert torch.nn.functional.cosine_similarity(got, ref).min() >= COS_MIN
+    rel = (hid - ref_hid).flatten(1).norm(dim=1) / ref_hid.flatten(1).norm(dim=1)
+    assert rel.max() < 5e-3, rel
+
+
 def test_fp16_range_overflow_falls_back_to_bf16(cuda_device):
     """A checkpoint with a weight beyond +-65504 cannot be stored in fp16: set_weight reports VLMFW_E_RANGE and the
     engine rebuilds the tower with bf16 operands instead of silently producing inf."""
