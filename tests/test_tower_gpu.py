@@ -79,16 +79,17 @@ def test_fp32_residual_stream_mode(cuda_device, monkeypatch, name):
 @pytest.mark.parametrize("residual", ["16", "32"])
 def test_massive_activation_channels(cuda_device, monkeypatch, name, residual):
     """Real ViT checkpoints carry a few residual-stream channels hundreds of times larger than the rest. The fp16 stream
-    must hold them (range 65504, relative precision 2^-11 at any magnitude): a position embedding with three channels at
-    +-300 (the stream keeps them through every layer) against the fp32 oracle, both stream modes."""
+    must hold them (range 65504, relative precision 2^-11 at any magnitude): the first layer's attention output bias
+    puts +-300 into three channels (the stream keeps them through every later layer) — against the fp32 oracle, both
+    stream modes."""
     spec = specs.SPECS[name]
     sd = weights.seeded_hf_state_dict(spec, 4)
-    key = next(k for k in sd if k.endswith("position_embedding.weight") or k.endswith("position_embedding"))
-    pos = sd[key].clone()
-    pos[..., 0] += 300.0
-    pos[..., 5] -= 300.0
-    pos[..., spec.hidden - 1] += 150.0
-    sd[key] = pos
+    key = next(k for k in sd if "layers.0.self_attn." in k and k.endswith(("out_proj.bias", "projection.bias")))
+    bias = sd[key].clone()
+    bias[0] += 300.0
+    bias[5] -= 300.0
+    bias[spec.hidden - 1] += 150.0
+    sd[key] = bias
     monkeypatch.setenv("VLMFW_RESIDUAL", residual)
     eng = TowerEngine(spec, "cuda:0")
     eng.load_hf_state_dict(sd)
