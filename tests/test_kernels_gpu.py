@@ -272,7 +272,9 @@ def test_layernorm_inplace_f32(cuda_device):
 
 
 @pytest.mark.parametrize("batch,tokens,heads,dh", [(2, 256, 16, 72), (2, 577, 16, 64), (2, 257, 16, 88), (3, 16, 2, 72),
-                                                  (3, 26, 2, 64), (3, 17, 2, 88), (1, 64, 1, 64), (1, 65, 3, 8)])
+                                                  (3, 26, 2, 64), (3, 17, 2, 88), (1, 64, 1, 64), (1, 65, 3, 8),
+                                                  # 64 k + 1 tokens: a last key block with a single key
+                                                  (2, 193, 2, 64), (2, 385, 3, 72), (3, 321, 2, 88), (2, 129, 2, 72)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_attention(cuda_device, batch, tokens, heads, dh, dtype):
     d = heads * dh
