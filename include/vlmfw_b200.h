@@ -224,6 +224,13 @@ int vlmfw_probe_adamw_ex(float* params, float* exp_avg, float* exp_avg_sq, const
                          float eps, float weight_decay, void* stream);
 int vlmfw_probe_bn_running_update(float* running_mean, float* running_var, const double* stats, int32_t dim,
                                   int32_t n_global, float momentum, void* stream);
+/* Dropout keep mask of the train-mode heads (nn.Dropout(p) in make_head / make_head_deeper,
+ * probing/models/base_probe.py:7-22), drawn on the device: keep [rows, cols] uint8 (16-byte aligned), 1 = kept.
+ * keep[r, c] is a function of (key, row0 + r, c) only — a counter-based generator — so the rank that owns global rows
+ * [row0, row0 + rows) draws exactly its slice of the single-process mask; the caller folds seed, step and task into key.
+ * P(keep) = 1 - dropout_p. The result feeds keep_mask / keep1 / keep2 of the *_grads entry points above. */
+int vlmfw_dropout_keep_mask(uint8_t* keep, int32_t rows, int32_t cols, int64_t row0, uint64_t key, float dropout_p,
+                            void* stream);
 
 /* ------------------------------------------------------------------ tester sink
  * Per-task confusion counts of a batch of predictions, accumulated on the device: counts [tasks, classes, classes] int32

@@ -130,3 +130,30 @@ def reference_multitask_steps(states: Dict[str, Dict[str, torch.Tensor]], tasks:
         history.append(losses)
     out = {t: {k: (v.float() if v.is_floating_point() else v) for k, v in heads[t].state_dict().items()} for t in tasks}
     return out, history
+
+
+# ---- dropout keep mask -----------------------------------------------------------------------------------------------
+# The reference draws nn.Dropout's mask from torch's global generator (probing/models/base_probe.py:7-22 builds
+# ``nn.Dropout(p)``); nothing downstream depends on WHICH mask is drawn, only on it being Bernoulli(1 - p) per element.
+# The CUDA path draws it with a counter-based generator (csrc/probe.cu dropout_mask_kernel) so that it is the same for
+# any sharding of the batch; this is that generator in numpy, element for element, for the bit-exact parity test.
+def _splitmix64(z):
+    import numpy as np
+
+    z = (z + np.uint64(0x9E3779B97F4A7C15))
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def keep_mask_reference(rows: int, cols: int, row0: int, key: int, dropout_p: float) -> torch.Tensor:
+    """uint8 [rows, cols]: keep[r, c] = (high 32 bits of splitmix64(splitmix64(key) ^ ((row0 + r) * cols + c))) >= p * 2^32."""
+    import numpy as np
+
+    with np.errstate(over="ignore"):
+        k = _splitmix64(np.array([key & 0xFFFFFFFFFFFFFFFF], dtype=np.uint64))[0]
+        idx = (np.uint64(row0) * np.uint64(cols) + np.arange(rows * cols, dtype=np.uint64))
+        u = (_splitmix64(k ^ idx) >> np.uint64(32)).astype(np.uint64)
+    t = float(np.float32(dropout_p)) * 4294967296.0
+    thr = 0xFFFFFFFF if t >= 4294967295.0 else int(t)
+    return torch.from_numpy((u >= np.uint64(thr)).astype(np.uint8).reshape(rows, cols))

@@ -113,3 +113,23 @@ def test_phase_split_equals_reference_step():
                                rtol=1e-5, atol=1e-6)
     torch.testing.assert_close((0.9 * state["0.running_var"].double() + 0.1 * var_unb).float(),
                                ref_state["0.running_var"], rtol=1e-5, atol=1e-6)
+
+
+KEEP_KAT = [0, 0, 1, 1, 1, 0, 1, 1, 1, 0, 1, 1, 1, 1, 0, 1]  # computed independently with Python integers
+
+
+def test_keep_mask_generator_properties():
+    """The counter-based dropout generator (restated in numpy; the CUDA kernel is compared with it bit for bit on the
+    GPU): slices of the global mask, Bernoulli(1 - p) rate, fresh draw per key."""
+    n, d, p = 512, 1152, 0.3
+    full = probe_oracle.keep_mask_reference(n, d, 0, 12345, p)
+    for lo, hi in [(0, 171), (171, 342), (342, 512), (511, 512)]:
+        assert torch.equal(probe_oracle.keep_mask_reference(hi - lo, d, lo, 12345, p), full[lo:hi])
+    assert abs(full.float().mean().item() - (1 - p)) < 4 * (p * (1 - p) / (n * d)) ** 0.5
+    other = probe_oracle.keep_mask_reference(n, d, 0, 12346, p)
+    assert abs((other == full).float().mean().item() - (p * p + (1 - p) ** 2)) < 0.01
+    assert bool(probe_oracle.keep_mask_reference(4, 7, 0, 1, 0.0).all())
+    # known-answer vector: pins the generator itself (splitmix64 constants, key mixing, threshold) against regressions
+    assert probe_oracle.keep_mask_reference(2, 8, 3, 42, 0.5).flatten().tolist() == KEEP_KAT
+    # splitmix64's published first output for state 0
+    assert int(probe_oracle._splitmix64(np.array([0], dtype=np.uint64))[0]) == 0xE220A8397B1DCDAF

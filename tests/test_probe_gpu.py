@@ -7,7 +7,7 @@ pytestmark = pytest.mark.gpu
 
 from oracle import probe_oracle, tower_oracle as O  # noqa: E402
 from vlmfw_b200 import probes  # noqa: E402
-from vlmfw_b200.probe_train import ProbeTrainStep  # noqa: E402
+from vlmfw_b200.probe_train import ProbeTrainStep, device_keep_mask, mask_key  # noqa: E402
 
 LOGIT_TOL = 1e-2  # BASELINE.json north_star: probe-logit max abs error
 
@@ -102,3 +102,37 @@ def test_sharded_phases_equal_single_process_gradient(cuda_device):
                                      state["0.bias"].cpu(), state["2.weight"].cpu(), state["2.bias"].cpu(), None,
                                      keep.cpu(), p)
     torch.testing.assert_close(total.cpu().double(), ref, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("rows,cols,row0,p", [(256, 1152, 0, 0.3), (7, 144, 1000003, 0.5), (1, 5, 0, 0.3),
+                                               (33, 512, 12345678901, 0.1), (0, 1152, 4, 0.3), (64, 1408, 192, 0.0),
+                                               (3, 17, 2, 0.999)])
+def test_device_keep_mask_matches_generator_restatement(cuda_device, rows, cols, row0, p):
+    """The device dropout mask equals its numpy restatement bit for bit (ragged tails, 64-bit element indices)."""
+    from vlmfw_b200 import _lib
+
+    key = mask_key(7, 41, 3)
+    got = device_keep_mask(_lib.load(), cuda_device, rows, cols, row0, key, p).cpu()
+    assert torch.equal(got, probe_oracle.keep_mask_reference(rows, cols, row0, key, p))
+    if p == 0.0:
+        assert bool(got.all())
+
+
+def test_device_keep_mask_is_shard_invariant_and_bernoulli(cuda_device):
+    from vlmfw_b200 import _lib
+
+    lib, n, d, p = _lib.load(), 2048, 1152, 0.3
+    full = device_keep_mask(lib, cuda_device, n, d, 0, mask_key(1, 5), p)
+    for lo, hi in [(0, 683), (683, 1366), (1366, 2048), (5, 6), (2047, 2048)]:
+        assert torch.equal(device_keep_mask(lib, cuda_device, hi - lo, d, lo, mask_key(1, 5), p), full[lo:hi])
+    rate = full.float().mean().item()
+    assert abs(rate - (1 - p)) < 4 * (p * (1 - p) / (n * d)) ** 0.5 + 1e-4  # 4 sigma of a Bernoulli mean
+    # per-column and per-row keep rates show no structure
+    assert (full.float().mean(0) - (1 - p)).abs().max().item() < 0.06
+    assert (full.float().mean(1) - (1 - p)).abs().max().item() < 0.08
+    other = device_keep_mask(lib, cuda_device, n, d, 0, mask_key(1, 6), p)  # next step: a fresh draw
+    agree = (other == full).float().mean().item()
+    assert abs(agree - (p * p + (1 - p) * (1 - p))) < 0.01
+    ts = ProbeTrainStep(d, 9, device=cuda_device, dropout_p=p, seed=1)
+    ts.step_count = 5
+    assert torch.equal(ts.dropout_keep_mask(n, 100, 356), full[100:356])

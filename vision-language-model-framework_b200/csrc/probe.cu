@@ -392,3 +392,53 @@ extern "C" int vlmfw_probe_bn_running_update(float* running_mean, float* running
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
+
+// Dropout keep mask, generated where it is consumed. keep[r, c] depends only on (key, GLOBAL row row0 + r, c): a
+// counter-based generator (splitmix64 finaliser over the element's global index), so a rank that holds rows
+// [row0, row0 + rows) of the batch draws exactly the slice of the single-process mask — the property the sharded train
+// step rests on — without anybody materialising the global mask (the host generator it replaces drew n_global x cols
+// numbers on every rank and copied its slice over PCIe each step). One thread = 16 consecutive bytes = one 128-bit store.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ out, int64_t total, int32_t cols, int64_t row0, uint64_t key,
+                                    uint32_t threshold) {
+    const int64_t first = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 16;
+    if (first >= total) return;
+    const uint64_t base = static_cast<uint64_t>(row0) * static_cast<uint64_t>(cols) + static_cast<uint64_t>(first);
+    const uint64_t k = splitmix64(key);
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {  // one hash per element, keyed by the element's GLOBAL index
+        const uint32_t u = static_cast<uint32_t>(splitmix64(k ^ (base + j)) >> 32);
+        w[j >> 2] |= (u >= threshold ? 1u : 0u) << (8 * (j & 3));
+    }
+    if (first + 16 <= total) {
+        *reinterpret_cast<uint4*>(out + first) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        for (int j = 0; first + j < total; ++j) out[first + j] = static_cast<uint8_t>((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+    }
+}
+
+extern "C" int vlmfw_dropout_keep_mask(uint8_t* keep, int32_t rows, int32_t cols, int64_t row0, uint64_t key,
+                                       float dropout_p, void* stream) {
+    VLMFW_REQUIRE(rows >= 0 && cols > 0 && row0 >= 0 && dropout_p >= 0.f && dropout_p < 1.f,
+                  "dropout_keep_mask: bad arguments");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    if (rows == 0) return VLMFW_OK;  // a rank that owns no row of this batch
+    VLMFW_REQUIRE(keep && (reinterpret_cast<uintptr_t>(keep) & 15) == 0, "dropout_keep_mask: keep must be a 16-byte aligned device pointer");
+    const int64_t total = static_cast<int64_t>(rows) * cols;
+    // keep <=> u >= p * 2^32 with u uniform on [0, 2^32): P(keep) = 1 - p to within 2^-32
+    const double t = static_cast<double>(dropout_p) * 4294967296.0;
+    const uint32_t threshold = t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
+    const int64_t threads = (total + 15) / 16;
+    dropout_mask_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        keep, total, cols, row0, key, threshold);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}

@@ -11,8 +11,9 @@ ranks and all-reducing between the phases lands on exactly the single-process st
     3. vlmfw_probe_adamw + vlmfw_probe_bn_running_update (identical on every rank)
 
 The reference's fp16 autocast + GradScaler (base_trainer.py:32,67-69) is a no-op for the result at these magnitudes
-and is not reproduced: everything here is fp32. Dropout masks are keyed by (seed, step, GLOBAL row) so the sharded and
-the single-process step draw the same mask.
+and is not reproduced: everything here is fp32. Dropout masks come from a counter-based generator on the device keyed by
+(seed, step, task, GLOBAL row, column) — vlmfw_dropout_keep_mask — so the sharded and the single-process step draw the
+same mask and every rank draws only its own rows.
 """
 from __future__ import annotations
 
@@ -22,6 +23,21 @@ import torch
 
 from . import _lib
 from .parallel import allreduce_sum_, shard_range
+
+
+def mask_key(seed: int, step: int, task_index: int = 0) -> int:
+    """64-bit key of one dropout draw: (seed, optimisation step, task); the second dropout of a deeper head uses key + 1."""
+    return (((seed * 1000003 + step) * 131 + task_index) * 2) & 0xFFFFFFFFFFFFFFFF
+
+
+def device_keep_mask(lib, device, rows: int, cols: int, row0: int, key: int, p: float) -> torch.Tensor:
+    """uint8 [rows, cols] keep mask of global rows [row0, row0 + rows), drawn on the device (vlmfw_dropout_keep_mask):
+    nothing crosses PCIe and no rank draws more than its own rows."""
+    keep = torch.empty(rows, cols, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        _lib.check(lib.vlmfw_dropout_keep_mask(keep.data_ptr(), rows, cols, row0, key & 0xFFFFFFFFFFFFFFFF, float(p),
+                                               torch.cuda.current_stream(device).cuda_stream))
+    return keep
 
 
 class ProbeTrainStep:
@@ -99,9 +115,8 @@ class ProbeTrainStep:
         """uint8 [hi-lo, D]; row r of the GLOBAL batch always gets the same mask regardless of the sharding."""
         if self.dropout_p <= 0.0:
             return None
-        g = torch.Generator(device="cpu").manual_seed(self.seed * 1000003 + self.step_count)
-        full = torch.rand(n_global, self.dim, generator=g) >= self.dropout_p
-        return full[lo:hi].to(torch.uint8).to(self.device).contiguous()
+        return device_keep_mask(self._lib, self.device, hi - lo, self.dim, lo, mask_key(self.seed, self.step_count),
+                                self.dropout_p)
 
     # ---- the three phases (exposed separately so tests can drive emulated ranks on one GPU) ----------------------
     def _prep(self, x, y):
@@ -291,11 +306,10 @@ class MultiTaskProbeTrainStep:
         """(keep1 [rows, D], keep2 [rows, Hd] or None), keyed by (seed, step, task, GLOBAL row)."""
         if self.dropout_p <= 0.0:
             return None, None
-        g = torch.Generator(device="cpu").manual_seed((self.seed * 1000003 + self.step_count) * 131 + task_index)
-        k1 = (torch.rand(n_global, self.dim, generator=g) >= self.dropout_p)[lo:hi]
-        k2 = (torch.rand(n_global, self.hidden, generator=g) >= self.dropout_p)[lo:hi] if self.hidden else None
-        dev = lambda m: None if m is None else m.to(torch.uint8).to(self.device).contiguous()  # noqa: E731
-        return dev(k1), dev(k2)
+        key = mask_key(self.seed, self.step_count, task_index)
+        k1 = device_keep_mask(self._lib, self.device, hi - lo, self.dim, lo, key, self.dropout_p)
+        k2 = device_keep_mask(self._lib, self.device, hi - lo, self.hidden, lo, key + 1, self.dropout_p) if self.hidden else None
+        return k1, k2
 
     # ---- phases -------------------------------------------------------------------------------------------------
     def phase1_stats(self, x: torch.Tensor) -> torch.Tensor:
