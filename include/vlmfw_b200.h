@@ -231,6 +231,18 @@ int vlmfw_probe_bn_running_update(float* running_mean, float* running_var, const
  * P(keep) = 1 - dropout_p. The result feeds keep_mask / keep1 / keep2 of the *_grads entry points above. */
 int vlmfw_dropout_keep_mask(uint8_t* keep, int32_t rows, int32_t cols, int64_t row0, uint64_t key, float dropout_p,
                             void* stream);
+/* Graph-replayable forms: the only things that change from one optimisation step to the next — AdamW's step number
+ * (bias corrections) and the per-step part of the dropout key — are read from a device-side counter, *steps_done =
+ * optimisation steps completed so far, which vlmfw_counter_add advances at the end of the step. With them one train step
+ * (probing/train/base_trainer.py:166-181) is a fixed launch sequence and replays from ONE CUDA graph, all-reduces and
+ * the loss read-back included. vlmfw_probe_adamw_dev performs step number *steps_done + 1; vlmfw_dropout_keep_mask_dev
+ * uses the key  key + *steps_done * step_stride. */
+int vlmfw_probe_adamw_dev(float* params, float* exp_avg, float* exp_avg_sq, const float* bucket, int64_t numel,
+                          int64_t weight_sum_index, const int64_t* steps_done, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, void* stream);
+int vlmfw_dropout_keep_mask_dev(uint8_t* keep, int32_t rows, int32_t cols, int64_t row0, uint64_t key,
+                                const int64_t* steps_done, uint64_t step_stride, float dropout_p, void* stream);
+int vlmfw_counter_add(int64_t* counter, int64_t inc, void* stream);
 
 /* ------------------------------------------------------------------ tester sink
  * Per-task confusion counts of a batch of predictions, accumulated on the device: counts [tasks, classes, classes] int32

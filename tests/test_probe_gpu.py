@@ -136,3 +136,43 @@ def test_device_keep_mask_is_shard_invariant_and_bernoulli(cuda_device):
     ts = ProbeTrainStep(d, 9, device=cuda_device, dropout_p=p, seed=1)
     ts.step_count = 5
     assert torch.equal(ts.dropout_keep_mask(n, 100, 356), full[100:356])
+
+
+@pytest.mark.parametrize("p", [0.3, 0.0])
+def test_graph_step_equals_eager_step(cuda_device, p):
+    """The train step replayed from one CUDA graph (device-side step counter for AdamW's bias corrections and the dropout
+    key) = the eager step: same masks bit for bit, same losses and parameters (bias corrections come from the device's
+    powf instead of the host's), also when eager and graph steps alternate."""
+    d, c, n, steps = 1152, 9, 256, 6
+    g = torch.Generator().manual_seed(5)
+    cw = torch.rand(c, generator=g) + 0.5
+    xs = [(torch.randn(n, d, generator=g) * 1.3 + 0.2).cuda() for _ in range(steps)]
+    ys = [torch.randint(-1, c, (n,), generator=g).cuda() for _ in range(steps)]
+    eager = ProbeTrainStep(d, c, device=cuda_device, class_weight=cw, dropout_p=p, seed=3)
+    graph = ProbeTrainStep(d, c, device=cuda_device, class_weight=cw, dropout_p=p, seed=3)
+    mixed = ProbeTrainStep(d, c, device=cuda_device, class_weight=cw, dropout_p=p, seed=3)
+    graph.capture(n)
+    with pytest.raises(ValueError):
+        graph.step_graph(xs[0][:7], ys[0][:7])
+    mixed.step(xs[0], ys[0])  # one eager step BEFORE capture: the counter starts at 1
+    mixed.capture(n)
+    for s in range(steps):
+        le = eager.step(xs[s], ys[s])
+        if p > 0:
+            # the mask the graph is about to draw from the device counter = the eager mask of this step
+            assert graph.step_count == s
+        lg = graph.step_graph(xs[s].cpu().pin_memory() if s % 2 else xs[s], ys[s])
+        if p > 0:
+            eager.step_count -= 1
+            assert torch.equal(graph._g_keep, eager.dropout_keep_mask(n, 0, n))
+            eager.step_count += 1
+        assert abs(le - lg) <= 1e-6 * max(1.0, abs(le))
+        if s >= 1:
+            lm = mixed.step_graph(xs[s], ys[s]) if s % 2 else mixed.step(xs[s], ys[s])
+            assert abs(le - lm) <= 1e-6 * max(1.0, abs(le))
+    for other in (graph, mixed):
+        assert other.step_count == eager.step_count == steps
+        torch.testing.assert_close(other.params, eager.params, rtol=0, atol=2e-7)
+        torch.testing.assert_close(other.exp_avg_sq, eager.exp_avg_sq, rtol=1e-6, atol=1e-12)
+        torch.testing.assert_close(other.running_var, eager.running_var, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(graph.last_logits, eager.last_logits, rtol=1e-5, atol=1e-6)

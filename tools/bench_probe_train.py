@@ -11,7 +11,9 @@ backward -> AdamW(lr 1e-4, wd 1e-4), the loss read back every step as the refere
 
 Arms, all on the same cached features (synthetic: N(0.2, 1.3) rows, labels uniform with 5 % of -1):
   * ``value``        ProbeTrainStep (vlmfw_probe_* kernels, two NCCL all-reduces per step: BatchNorm sums [2D] fp64 and
-                     the flat gradient bucket), features already resident in HBM; CUDA events, max over ranks;
+                     the flat gradient bucket) replayed from one CUDA graph per step (``capture`` / ``step_graph``),
+                     features already resident in HBM; CUDA events, max over ranks; ``eager`` = the same kernels
+                     launched one by one (``step``);
   * ``e2e``          the same through host batches: pinned-host -> device copy of the rank's [256, 1152] fp32 rows and
                      labels inside the timed region, like the reference's ``x.to(device)`` of a DataLoader batch;
   * ``torch_gpu``    (rank 0, after the timed runs) the reference's loop as it stands — torch modules, fp16 autocast +
@@ -85,6 +87,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--pool", type=int, default=32, help="distinct cached batches cycled through")
     ap.add_argument("--no-baselines", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time only the eager launches")
     args = ap.parse_args()
 
     env = parallel.init_distributed("nccl")
@@ -106,17 +109,20 @@ def main():
     xs_dev = [x.to(dev) for x in xs_host]
     ys_dev = [y.to(dev) for y in ys_host]
 
-    def timed(resident: bool):
+    def timed(resident: bool, use_graph: bool):
         ts = ProbeTrainStep(D, C, device=dev, class_weight=cw, dropout_p=P_DROP, seed=3)
+        if use_graph:
+            ts.capture(hi - lo, n_global=nb, global_offset=lo)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         loss = 0.0
 
         def one(i):
             j = i % args.pool
-            if resident:
-                x, y = xs_dev[j], ys_dev[j]
-            else:
-                x, y = xs_host[j].to(dev, non_blocking=True), ys_host[j].to(dev, non_blocking=True)
+            x, y = (xs_dev[j], ys_dev[j]) if resident else (xs_host[j], ys_host[j])
+            if use_graph:
+                return ts.step_graph(x, y)  # stages x / y (device or pinned host) into the graph's input buffers
+            if not resident:
+                x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
             return ts.step(x, y, n_global=nb, global_offset=lo)
 
         for i in range(args.warmup):
@@ -135,10 +141,23 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if env.is_distributed:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), KERNELS_PER_STEP * args.steps, loss, ts
+        return ms.item(), loss, ts
 
-    ms_res, launches, loss_res, ts = timed(True)
-    ms_e2e, _, loss_e2e, _ = timed(False)
+    ms_eager, loss_eager, ts = timed(True, False)
+    ms_eager_e2e, _, _ = timed(False, False)
+    graph_err = None
+    try:
+        if args.no_graph:
+            raise RuntimeError("--no-graph")
+        ms_res, loss_res, _ = timed(True, True)
+        ms_e2e, loss_e2e, _ = timed(False, True)
+    except Exception as e:  # capture of the NCCL collectives refused: report the eager launches of the same kernels
+        if env.is_distributed and not args.no_graph:
+            raise  # ranks must not diverge
+        graph_err = repr(e)
+        print(f"[bench_probe_train] CUDA graph capture failed ({e}); reporting eager launches", file=sys.stderr)
+        ms_res, loss_res, ms_e2e, loss_e2e = ms_eager, loss_eager, ms_eager_e2e, loss_eager
+    launches = (KERNELS_PER_STEP + 1) * args.steps  # + the step-counter kernel of the graph form
 
     if env.rank == 0:
         res = {
@@ -152,10 +171,13 @@ def main():
                        "global_batch": nb, "parallelism": f"dp{env.world}",
                        "exchange": "2 NCCL all-reduces per step (BatchNorm sums, gradient bucket)",
                        "allreduce_bytes_per_step": 2 * D * 8 + (ts.n_params + 2) * 4,
-                       "loss_read_back_every_step": True},
+                       "loss_read_back_every_step": True, "cuda_graph": graph_err is None},
+            "eager": {"value": round(args.steps / (ms_eager / 1e3), 1), "e2e": round(args.steps / (ms_eager_e2e / 1e3), 1),
+                      "unit": "steps/s", "what": "the same kernels launched one by one (ProbeTrainStep.step)",
+                      "final_loss": round(loss_eager, 6)},
             "e2e": {"value": round(args.steps / (ms_e2e / 1e3), 1), "unit": "steps/s",
                     "h2d_bytes_per_step": B_LOCAL * D * 4 + B_LOCAL * 8, "d2h_bytes_per_step": 8,
-                    "api": "ProbeTrainStep.step(host batch .to(device))"},
+                    "api": "ProbeTrainStep.step_graph(pinned host batch)"},
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
             "final_loss": round(loss_res, 6), "final_loss_e2e": round(loss_e2e, 6),
         }
@@ -173,6 +195,7 @@ def main():
             res["torch_gpu"] = {"value": round(sps, 1), "unit": "steps/s", "gpus": 1, "batch": nb,
                                 "what": "reference loop (torch modules, fp16 autocast + GradScaler, AdamW) on one GPU, "
                                         "global batch per step, host batches"}
+        if not args.no_baselines and not env.is_distributed:  # host-core baseline at N = 1 only (torchrun pins OMP to 1 thread)
             torch.set_num_threads(os.cpu_count() or 1)
             xs_c = [x.clone() for x in xs_full]
             ys_c = [y.clone() for y in ys_full]

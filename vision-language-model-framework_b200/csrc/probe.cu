@@ -89,18 +89,39 @@ __global__ void __launch_bounds__(256) probe_forward_kernel(const float* __restr
 
 // ------------------------------------------------------------------------------------------------ train step
 // stats[d] = sum_b x[b,d], stats[dim+d] = sum_b x[b,d]^2 in fp64 (the variance is a difference of these).
-__global__ void __launch_bounds__(128) bn_stats_kernel(const float* __restrict__ x, int batch, int dim,
-                                                       double* __restrict__ stats) {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= dim) return;
+// A block owns 32 feature columns (lane = column: every warp load is one 128-byte line); its STAT_WARPS warps deal the
+// rows round-robin and their partials are combined in warp order through shared memory — a fixed summation order, so
+// the result does not depend on scheduling. (The first version ran ONE thread per column over all rows on 9 blocks:
+// a 256-deep chain of dependent L2 round trips, ~20x the time of everything else in the step.)
+constexpr int STAT_WARPS = 16;
+__global__ void __launch_bounds__(32 * STAT_WARPS) bn_stats_kernel(const float* __restrict__ x, int batch, int dim,
+                                                                   double* __restrict__ stats) {
+    __shared__ double ss[STAT_WARPS][32];
+    __shared__ double sq[STAT_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = blockIdx.x * 32 + lane;
     double s = 0.0, q = 0.0;
-    for (int b = 0; b < batch; ++b) {
-        const double v = static_cast<double>(x[static_cast<size_t>(b) * dim + d]);
-        s += v;
-        q += v * v;
+    if (d < dim) {
+#pragma unroll 4
+        for (int b = warp; b < batch; b += STAT_WARPS) {
+            const double v = static_cast<double>(x[static_cast<size_t>(b) * dim + d]);
+            s += v;
+            q += v * v;
+        }
     }
-    stats[d] = s;
-    stats[dim + d] = q;
+    ss[warp][lane] = s;
+    sq[warp][lane] = q;
+    __syncthreads();
+    if (warp == 0 && d < dim) {
+        double st = 0.0, qt = 0.0;
+#pragma unroll
+        for (int w = 0; w < STAT_WARPS; ++w) {
+            st += ss[w][lane];
+            qt += sq[w][lane];
+        }
+        stats[d] = st;
+        stats[dim + d] = qt;
+    }
 }
 
 struct TrainArgs {
@@ -180,76 +201,87 @@ __global__ void __launch_bounds__(256) probe_train_fwd_kernel(TrainArgs a) {
     }
 }
 
-// Phase B: one thread per feature column d, fixed-order loop over the batch (deterministic sums).
-// bucket = [dW (C*D) | db (C) | dgamma (D) | dbeta (D) | loss_sum | weight_sum]
-__global__ void __launch_bounds__(128) probe_train_bwd_kernel(TrainArgs a) {
-    extern __shared__ float bsm[];  // dlogits [B*C]
+// Phase B: a block owns 32 feature columns (lane = column), its BWD_WARPS warps deal the batch rows round-robin; the
+// per-warp partial sums of (dW[c][d], dgamma[d], dbeta[d]) meet in shared memory and are added in warp order — fixed
+// summation order, deterministic. bucket = [dW (C*D) | db (C) | dgamma (D) | dbeta (D) | loss_sum | weight_sum]
+constexpr int BWD_WARPS = 8;
+__global__ void __launch_bounds__(32 * BWD_WARPS) probe_train_bwd_kernel(TrainArgs a) {
+    extern __shared__ float bsm[];  // dlogits [B*C] | partials [BWD_WARPS][C + 2][32]
     const int nd = a.batch * a.classes;
     for (int i = threadIdx.x; i < nd; i += blockDim.x) bsm[i] = a.scratch[i];
     __syncthreads();
     const int C = a.classes, D = a.dim;
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d < D) {
-        float mean, rstd;
-        bn_mean_rstd(a.stats, D, d, a.n_global, a.bn_eps, mean, rstd);
-        const float gm = a.gamma[d], bt = a.beta[d];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = blockIdx.x * 32 + lane;
+    float* part = bsm + ((nd + 31) & ~31);
+    {
         float wcol[MAX_CLASSES];
         float dw[MAX_CLASSES];
+        float dgamma = 0.f, dbeta = 0.f;
 #pragma unroll
         for (int c = 0; c < MAX_CLASSES; ++c) {
-            wcol[c] = c < C ? a.weight[static_cast<size_t>(c) * D + d] : 0.f;
+            wcol[c] = (c < C && d < D) ? a.weight[static_cast<size_t>(c) * D + d] : 0.f;
             dw[c] = 0.f;
         }
-        float dgamma = 0.f, dbeta = 0.f;
-        for (int b = 0; b < a.batch; ++b) {
-            const float xh = (a.x[static_cast<size_t>(b) * D + d] - mean) * rstd;
-            float keep = 1.f;
-            if (a.keep != nullptr) keep = a.keep[static_cast<size_t>(b) * D + d] ? a.keep_scale : 0.f;
-            const float z = (xh * gm + bt) * keep;
-            float dz = 0.f;
+        if (d < D) {
+            float mean, rstd;
+            bn_mean_rstd(a.stats, D, d, a.n_global, a.bn_eps, mean, rstd);
+            const float gm = a.gamma[d], bt = a.beta[d];
+#pragma unroll 2
+            for (int b = warp; b < a.batch; b += BWD_WARPS) {
+                const float xh = (a.x[static_cast<size_t>(b) * D + d] - mean) * rstd;
+                float keep = 1.f;
+                if (a.keep != nullptr) keep = a.keep[static_cast<size_t>(b) * D + d] ? a.keep_scale : 0.f;
+                const float z = (xh * gm + bt) * keep;
+                float dz = 0.f;
 #pragma unroll
-            for (int c = 0; c < MAX_CLASSES; ++c) {
-                if (c < C) {
-                    const float g = bsm[b * C + c];
-                    dw[c] += g * z;
-                    dz += g * wcol[c];
+                for (int c = 0; c < MAX_CLASSES; ++c) {
+                    if (c < C) {
+                        const float g = bsm[b * C + c];
+                        dw[c] += g * z;
+                        dz += g * wcol[c];
+                    }
                 }
+                const float dy = dz * keep;
+                dgamma += dy * xh;
+                dbeta += dy;
             }
-            const float dy = dz * keep;
-            dgamma += dy * xh;
-            dbeta += dy;
         }
+        float* mine = part + static_cast<size_t>(warp) * (C + 2) * 32 + lane;
 #pragma unroll
         for (int c = 0; c < MAX_CLASSES; ++c)
-            if (c < C) a.bucket[static_cast<size_t>(c) * D + d] = dw[c];
-        a.bucket[static_cast<size_t>(C) * D + C + d] = dgamma;
-        a.bucket[static_cast<size_t>(C) * D + C + D + d] = dbeta;
+            if (c < C) mine[c * 32] = dw[c];
+        mine[C * 32] = dgamma;
+        mine[(C + 1) * 32] = dbeta;
+    }
+    __syncthreads();
+    if (d < D) {
+        for (int k = warp; k < C + 2; k += BWD_WARPS) {  // quantity k of column d: add the warps' partials in order
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < BWD_WARPS; ++w) t += part[(static_cast<size_t>(w) * (C + 2) + k) * 32 + lane];
+            const size_t at = k < C ? static_cast<size_t>(k) * D + d
+                                    : static_cast<size_t>(C) * D + C + static_cast<size_t>(k - C) * D + d;
+            a.bucket[at] = t;
+        }
     }
     if (blockIdx.x == 0) {
-        if (threadIdx.x < C) {
-            float s = 0.f;
-            for (int b = 0; b < a.batch; ++b) s += bsm[b * C + threadIdx.x];
-            a.bucket[static_cast<size_t>(C) * D + threadIdx.x] = s;
-        }
-        if (threadIdx.x == 32) {
-            const float* loss_b = a.scratch + static_cast<size_t>(a.batch) * C;
-            const float* w_b = loss_b + a.batch;
-            float ls = 0.f, ws = 0.f;
-            for (int b = 0; b < a.batch; ++b) {
-                ls += loss_b[b];
-                ws += w_b[b];
-            }
-            a.bucket[static_cast<size_t>(C) * D + C + 2 * D] = ls;
-            a.bucket[static_cast<size_t>(C) * D + C + 2 * D + 1] = ws;
+        // db[c] and the two loss sums: one warp per quantity, lanes stride the batch, xor-shuffle tree (fixed order)
+        const float* loss_b = a.scratch + static_cast<size_t>(a.batch) * C;
+        const float* w_b = loss_b + a.batch;
+        for (int k = warp; k < C + 2; k += BWD_WARPS) {
+            float t = 0.f;
+            for (int b = lane; b < a.batch; b += 32) t += k < C ? bsm[b * C + k] : (k == C ? loss_b[b] : w_b[b]);
+            t = warp_sum(t);
+            if (lane == 0) a.bucket[static_cast<size_t>(C) * D + (k < C ? k : C + 2 * D + (k - C))] = t;
         }
     }
 }
 
 // torch.optim.AdamW (decoupled weight decay), grad = bucket[i] / bucket[weight_sum_index]
-__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                                                    const float* __restrict__ bucket, int64_t numel,
-                                                    int64_t wsum_index, float lr, float beta1, float beta2, float eps,
-                                                    float wd, float bc1, float bc2_sqrt) {
+__device__ __forceinline__ void adamw_body(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                           const float* __restrict__ bucket, int64_t numel, int64_t wsum_index, float lr,
+                                           float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt) {
     const float wsum = bucket[wsum_index];
     const float inv = wsum > 0.f ? 1.f / wsum : 0.f;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < numel;
@@ -265,6 +297,28 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
         p[i] = pi;
     }
 }
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                    const float* __restrict__ bucket, int64_t numel,
+                                                    int64_t wsum_index, float lr, float beta1, float beta2, float eps,
+                                                    float wd, float bc1, float bc2_sqrt) {
+    adamw_body(p, m, v, bucket, numel, wsum_index, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+}
+
+// The same update with the step number read from device memory (steps completed so far; this is step *steps_done + 1):
+// nothing in the launch changes from one optimisation step to the next, so the whole train step replays from a CUDA graph.
+__global__ void __launch_bounds__(256) adamw_dev_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                        float* __restrict__ v, const float* __restrict__ bucket,
+                                                        int64_t numel, int64_t wsum_index,
+                                                        const int64_t* __restrict__ steps_done, float lr, float beta1,
+                                                        float beta2, float eps, float wd) {
+    const float step = static_cast<float>(*steps_done + 1);
+    const float bc1 = 1.f - powf(beta1, step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
+    adamw_body(p, m, v, bucket, numel, wsum_index, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+}
+
+__global__ void counter_add_kernel(int64_t* ctr, int64_t inc) { *ctr += inc; }
 
 // running_mean/var <- (1-momentum) * old + momentum * batch stat (unbiased variance), nn.BatchNorm1d train mode
 __global__ void bn_running_kernel(float* __restrict__ rm, float* __restrict__ rv, const double* __restrict__ stats,
@@ -319,7 +373,7 @@ extern "C" int vlmfw_probe_bn_stats(const float* x, int32_t batch, int32_t dim, 
     VLMFW_REQUIRE(x && stats && batch > 0 && dim > 0, "probe_bn_stats: bad arguments");
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
-    bn_stats_kernel<<<(dim + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, batch, dim, stats);
+    bn_stats_kernel<<<(dim + 31) / 32, 32 * STAT_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(x, batch, dim, stats);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
@@ -360,7 +414,12 @@ extern "C" int vlmfw_probe_linear_grads(const float* x, const int64_t* targets, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     probe_train_fwd_kernel<<<batch, 256, static_cast<size_t>(dim + classes) * sizeof(float), s>>>(a);
     VLMFW_LAUNCH_CHECK();
-    probe_train_bwd_kernel<<<(dim + 127) / 128, 128, static_cast<size_t>(batch) * classes * sizeof(float), s>>>(a);
+    const size_t bwd_smem = (((static_cast<size_t>(batch) * classes + 31) & ~static_cast<size_t>(31)) +
+                             static_cast<size_t>(BWD_WARPS) * (classes + 2) * 32) * sizeof(float);
+    static const cudaError_t bwd_attr = cudaFuncSetAttribute(probe_train_bwd_kernel,
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    VLMFW_CUDA_OK(bwd_attr);
+    probe_train_bwd_kernel<<<(dim + 31) / 32, 32 * BWD_WARPS, bwd_smem, s>>>(a);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
@@ -378,6 +437,30 @@ extern "C" int vlmfw_probe_adamw(float* params, float* exp_avg, float* exp_avg_s
     adamw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, exp_avg, exp_avg_sq, bucket, numel,
                                                                       weight_sum_index, lr, beta1, beta2, eps,
                                                                       weight_decay, bc1, bc2_sqrt);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+extern "C" int vlmfw_probe_adamw_dev(float* params, float* exp_avg, float* exp_avg_sq, const float* bucket, int64_t numel,
+                                     int64_t weight_sum_index, const int64_t* steps_done, float lr, float beta1,
+                                     float beta2, float eps, float weight_decay, void* stream) {
+    VLMFW_REQUIRE(params && exp_avg && exp_avg_sq && bucket && steps_done && numel > 0, "probe_adamw_dev: bad arguments");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    int grid = static_cast<int>((numel + 255) / 256);
+    if (grid > 1024) grid = 1024;
+    adamw_dev_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, exp_avg, exp_avg_sq, bucket, numel,
+                                                                          weight_sum_index, steps_done, lr, beta1, beta2,
+                                                                          eps, weight_decay);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+extern "C" int vlmfw_counter_add(int64_t* counter, int64_t inc, void* stream) {
+    VLMFW_REQUIRE(counter, "counter_add: bad arguments");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    counter_add_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(counter, inc);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
@@ -406,10 +489,12 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
 }
 
 __global__ void dropout_mask_kernel(uint8_t* __restrict__ out, int64_t total, int32_t cols, int64_t row0, uint64_t key,
-                                    uint32_t threshold) {
+                                    uint32_t threshold, const int64_t* __restrict__ steps_done, uint64_t step_stride) {
     const int64_t first = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 16;
     if (first >= total) return;
     const uint64_t base = static_cast<uint64_t>(row0) * static_cast<uint64_t>(cols) + static_cast<uint64_t>(first);
+    // graph replay: the per-step part of the key comes from the device-side step counter (key + steps_done * stride)
+    if (steps_done != nullptr) key += static_cast<uint64_t>(*steps_done) * step_stride;
     const uint64_t k = splitmix64(key);
     uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -424,8 +509,8 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ out, int64_t total, in
     }
 }
 
-extern "C" int vlmfw_dropout_keep_mask(uint8_t* keep, int32_t rows, int32_t cols, int64_t row0, uint64_t key,
-                                       float dropout_p, void* stream) {
+static int dropout_keep_mask_launch(uint8_t* keep, int32_t rows, int32_t cols, int64_t row0, uint64_t key,
+                                    const int64_t* steps_done, uint64_t step_stride, float dropout_p, void* stream) {
     VLMFW_REQUIRE(rows >= 0 && cols > 0 && row0 >= 0 && dropout_p >= 0.f && dropout_p < 1.f,
                   "dropout_keep_mask: bad arguments");
     int rc = device_check();
@@ -438,7 +523,19 @@ extern "C" int vlmfw_dropout_keep_mask(uint8_t* keep, int32_t rows, int32_t cols
     const uint32_t threshold = t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
     const int64_t threads = (total + 15) / 16;
     dropout_mask_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        keep, total, cols, row0, key, threshold);
+        keep, total, cols, row0, key, threshold, steps_done, step_stride);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
+}
+
+extern "C" int vlmfw_dropout_keep_mask(uint8_t* keep, int32_t rows, int32_t cols, int64_t row0, uint64_t key,
+                                       float dropout_p, void* stream) {
+    return dropout_keep_mask_launch(keep, rows, cols, row0, key, nullptr, 0, dropout_p, stream);
+}
+
+extern "C" int vlmfw_dropout_keep_mask_dev(uint8_t* keep, int32_t rows, int32_t cols, int64_t row0, uint64_t key,
+                                           const int64_t* steps_done, uint64_t step_stride, float dropout_p,
+                                           void* stream) {
+    VLMFW_REQUIRE(steps_done, "dropout_keep_mask_dev: steps_done is null");
+    return dropout_keep_mask_launch(keep, rows, cols, row0, key, steps_done, step_stride, dropout_p, stream);
 }

@@ -30,6 +30,9 @@ def mask_key(seed: int, step: int, task_index: int = 0) -> int:
     return (((seed * 1000003 + step) * 131 + task_index) * 2) & 0xFFFFFFFFFFFFFFFF
 
 
+MASK_KEY_STEP_STRIDE = 262  # mask_key(seed, step + 1, t) - mask_key(seed, step, t): what one step adds to the key
+
+
 def device_keep_mask(lib, device, rows: int, cols: int, row0: int, key: int, p: float) -> torch.Tensor:
     """uint8 [rows, cols] keep mask of global rows [row0, row0 + rows), drawn on the device (vlmfw_dropout_keep_mask):
     nothing crosses PCIe and no rank draws more than its own rows."""
@@ -162,6 +165,81 @@ class ProbeTrainStep:
         self.num_batches_tracked += 1
         tail = self.bucket[self.n_params:].tolist()  # [loss_sum, weight_sum] — the step's only D2H read
         return tail[0] / tail[1] if tail[1] > 0 else 0.0
+
+    # ---- the whole step as ONE CUDA graph -----------------------------------------------------------------------
+    def capture(self, b_local: int, n_global: Optional[int] = None, global_offset: int = 0) -> None:
+        """Capture one optimisation step for a fixed local batch size into a CUDA graph: the six kernels, the two
+        all-reduces (NCCL collectives are capturable) and the read-back of [loss_sum, weight_sum] into pinned host
+        memory. Nothing in the launch sequence depends on the step number: AdamW's bias corrections and the per-step
+        part of the dropout key are read from a device-side counter (vlmfw_probe_adamw_dev,
+        vlmfw_dropout_keep_mask_dev, vlmfw_counter_add). The step is launch-latency bound (six ~5 us kernels), so
+        replaying it costs one launch instead of six plus their host-side argument marshalling. ``step_graph`` then runs
+        the same arithmetic as ``step`` (same kernels, same masks); the eager ``step`` stays usable in between."""
+        import torch.distributed as dist
+
+        dev, d, c = self.device, self.dim, self.classes
+        n_global = b_local if n_global is None else n_global
+        self._g_shape = (b_local, n_global, global_offset)
+        self._g_x = torch.zeros(b_local, d, device=dev)
+        self._g_y = torch.full((b_local,), -1, dtype=torch.int64, device=dev)
+        self._g_keep = torch.empty(b_local, d, dtype=torch.uint8, device=dev) if self.dropout_p > 0.0 else None
+        self._g_logits = torch.empty(b_local, c, device=dev)
+        self._g_scratch = torch.empty(b_local * (c + 2), device=dev)
+        self._g_steps_done = torch.tensor([self.step_count], dtype=torch.int64, device=dev)
+        self._g_steps_done_value = self.step_count
+        self._g_loss = torch.zeros(2, dtype=torch.float32).pin_memory()
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if distributed:  # communicator set-up cannot be captured: run one collective of each dtype eagerly first
+            allreduce_sum_(torch.zeros(2, dtype=torch.float64, device=dev), self.group)
+            allreduce_sum_(torch.zeros(2, device=dev), self.group)
+        torch.cuda.synchronize(dev)
+        lib, key0 = self._lib, mask_key(self.seed, 0)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(dev), torch.cuda.graph(graph):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.vlmfw_probe_bn_stats(self._g_x.data_ptr(), b_local, d, self.stats.data_ptr(), st))
+            allreduce_sum_(self.stats, self.group)
+            if self._g_keep is not None:
+                _lib.check(lib.vlmfw_dropout_keep_mask_dev(self._g_keep.data_ptr(), b_local, d, global_offset, key0,
+                                                           self._g_steps_done.data_ptr(), MASK_KEY_STEP_STRIDE,
+                                                           float(self.dropout_p), st))
+            _lib.check(lib.vlmfw_probe_linear_grads(
+                self._g_x.data_ptr(), self._g_y.data_ptr(), b_local, d, c, self.stats.data_ptr(), n_global, self.bn_eps,
+                self.gamma.data_ptr(), self.beta.data_ptr(), self.weight.data_ptr(), self.bias.data_ptr(),
+                None if self.class_weight is None else self.class_weight.data_ptr(),
+                None if self._g_keep is None else self._g_keep.data_ptr(), self.dropout_p, self.bucket.data_ptr(),
+                self._g_logits.data_ptr(), self._g_scratch.data_ptr(), st))
+            allreduce_sum_(self.bucket, self.group)
+            _lib.check(lib.vlmfw_probe_adamw_dev(
+                self.params.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.bucket.data_ptr(),
+                self.n_params, self.n_params + 1, self._g_steps_done.data_ptr(), self.lr, self.betas[0], self.betas[1],
+                self.eps, self.wd, st))
+            _lib.check(lib.vlmfw_probe_bn_running_update(
+                self.running_mean.data_ptr(), self.running_var.data_ptr(), self.stats.data_ptr(), d, n_global,
+                self.bn_momentum, st))
+            _lib.check(lib.vlmfw_counter_add(self._g_steps_done.data_ptr(), 1, st))
+            self._g_loss.copy_(self.bucket[self.n_params:], non_blocking=True)
+        self._graph = graph
+
+    def step_graph(self, x: torch.Tensor, y: torch.Tensor) -> float:
+        """``step`` through the captured graph: stage this rank's rows (host or device tensors) into the graph's input
+        buffers, replay, wait for the loss. Shapes are the ones given to ``capture``."""
+        if getattr(self, "_graph", None) is None:
+            raise RuntimeError("step_graph before capture()")
+        if tuple(x.shape) != (self._g_shape[0], self.dim) or y.shape[0] != self._g_shape[0]:
+            raise ValueError(f"step_graph: batch {tuple(x.shape)} does not match the captured shape {self._g_shape[0]}")
+        if self._g_steps_done_value != self.step_count:  # eager steps ran in between
+            self._g_steps_done.fill_(self.step_count)
+        self._g_x.copy_(x, non_blocking=True)
+        self._g_y.copy_(y, non_blocking=True)
+        self._graph.replay()
+        self.last_logits = self._g_logits
+        self.step_count += 1
+        self._g_steps_done_value = self.step_count
+        self.num_batches_tracked += 1
+        torch.cuda.current_stream(self.device).synchronize()
+        loss_sum, weight_sum = self._g_loss.tolist()
+        return loss_sum / weight_sum if weight_sum > 0 else 0.0
 
     def step(self, x: torch.Tensor, y: torch.Tensor, n_global: Optional[int] = None, global_offset: int = 0,
              keep_mask: Optional[torch.Tensor] = None) -> float:
