@@ -146,11 +146,14 @@ def main():
     ms_eager, loss_eager, ts = timed(True, False)
     ms_eager_e2e, _, _ = timed(False, False)
     graph_err = None
+    graphed = []
     try:
         if args.no_graph:
             raise RuntimeError("--no-graph")
-        ms_res, loss_res, _ = timed(True, True)
-        ms_e2e, loss_e2e, _ = timed(False, True)
+        ms_res, loss_res, g1 = timed(True, True)
+        graphed.append(g1)
+        ms_e2e, loss_e2e, g2 = timed(False, True)
+        graphed.append(g2)
     except Exception as e:  # capture of the NCCL collectives refused: report the eager launches of the same kernels
         if env.is_distributed and not args.no_graph:
             raise  # ranks must not diverge
@@ -205,8 +208,16 @@ def main():
                                                               f"{min(args.steps, 50)} timed steps"}
         print(json.dumps(res), flush=True)
     if env.is_distributed:
+        # The N = 2 run of this script printed its line and then sat in the teardown until `timeout` killed it: the
+        # process group was being destroyed while CUDA graphs holding captured NCCL kernels were still alive. Release
+        # the graphs first, and leave without the communicator teardown (the line is out, nothing is left to flush).
+        for t in graphed:
+            t.release_graph()
+        torch.cuda.synchronize(dev)
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

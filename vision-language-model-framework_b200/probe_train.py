@@ -221,6 +221,11 @@ class ProbeTrainStep:
             self._g_loss.copy_(self.bucket[self.n_params:], non_blocking=True)
         self._graph = graph
 
+    def release_graph(self) -> None:
+        """Drop the captured graph (and with it the captured NCCL kernels). Call before
+        ``torch.distributed.destroy_process_group()``: tearing a communicator down under a live graph can block."""
+        self._graph = None
+
     def step_graph(self, x: torch.Tensor, y: torch.Tensor) -> float:
         """``step`` through the captured graph: stage this rank's rows (host or device tensors) into the graph's input
         buffers, replay, wait for the loss. Shapes are the ones given to ``capture``."""
