@@ -139,3 +139,41 @@ def test_parsed_attributes_shape():
     out = probes.parsed_attributes({"gender": torch.tensor([1, 0]), "hat": torch.tensor([0, 1])})
     assert out == [{"gender": 1, "hat": 0}, {"gender": 0, "hat": 1}]
     assert probes.parsed_attributes(torch.tensor([3, 4]), ["age"]) == [{"age": 3}, {"age": 4}]
+
+
+def test_sass_of_the_hot_kernels_is_tcgen05_and_tma():
+    """Static proof, no GPU needed: the shipped .so carries sm_100a SASS in which every GEMM and tensor-core attention
+    instantiation issues tcgen05 MMAs (UTCHMMA), is fed by TMA (UTMALDG), drains TMEM with tcgen05.ld (LDTM), and contains
+    no warp-level mma.sync (HMMA) — B200_PROFILING.md's mnemonics. The generic attention fallback is the one mma.sync
+    kernel and is not on the three towers' path."""
+    import re
+    import shutil
+    import subprocess
+
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    so = os.path.join(os.path.dirname(_lib.__file__), "libvlmfw_b200.so")
+    out = subprocess.run([tool, "-sass", so], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in out or "EF_CUDA_SM100" in out, "no sm_100a code object in the library"
+    per_fn = {}
+    name = None
+    for line in out.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            per_fn[name] = set()
+        elif name is not None:
+            m = re.match(r"\s*/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+            if m:
+                per_fn[name].add(m.group(1))
+    gemms = {f: ops for f, ops in per_fn.items() if "gemm_bf16_tn_kernel" in f}
+    atts = {f: ops for f, ops in per_fn.items() if "attention_tc_kernel" in f}
+    assert len(gemms) >= 6 and len(atts) >= 2, (len(gemms), len(atts))
+    for f, ops in {**gemms, **atts}.items():
+        assert "UTCHMMA" in ops, f"{f}: no tcgen05.mma"
+        assert "UTMALDG" in ops, f"{f}: operands not loaded by TMA"
+        assert "LDTM" in ops, f"{f}: accumulators not read back from TMEM"
+        assert not any(op.startswith("HMMA") for op in ops), f"{f}: mma.sync in a tcgen05 kernel"
+    assert any("UTMASTG" in ops for ops in gemms.values()), "no TMA store in any GEMM epilogue"
+    assert all("UTMASTG" in ops for ops in atts.values()), "attention epilogue does not store through TMA"
