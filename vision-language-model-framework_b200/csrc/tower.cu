@@ -63,7 +63,7 @@ const DevInfo& dev_info() {
             return d;
         }
         if (p.major != 10) {
-            snprintf(d.msg, sizeof(d.msg), "device %s is sm_%d%d; vlmfw_b200 kernels are sm_100a only", p.name, p.major,
+            snprintf(d.msg, sizeof(d.msg), "device %.160s is sm_%d%d; vlmfw_b200 kernels are sm_100a only", p.name, p.major,
                      p.minor);
             return d;
         }
@@ -379,7 +379,6 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
     void* patch_a = mid;
     const int D = t->D, I = t->I, S = t->S, P = t->P;
     const int M = batch * S;
-    const int act_dt = t->f16 ? VLMFW_DT_F16 : VLMFW_DT_BF16;
 
     // ---- embeddings: conv-as-GEMM (+bias +position embedding), class token, optional pre-LN
     bool head_done = false;  // xn / stats of the embeddings already produced by the patch GEMM's epilogue
