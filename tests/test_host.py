@@ -177,3 +177,25 @@ def test_sass_of_the_hot_kernels_is_tcgen05_and_tma():
         assert not any(op.startswith("HMMA") for op in ops), f"{f}: mma.sync in a tcgen05 kernel"
     assert any("UTMASTG" in ops for ops in gemms.values()), "no TMA store in any GEMM epilogue"
     assert all("UTMASTG" in ops for ops in atts.values()), "attention epilogue does not store through TMA"
+
+
+def test_train_step_entry_points_validate_arguments_without_a_gpu():
+    """Argument checks of the probe-training entry points come before any device work: bad arguments are E_INVALID with
+    a message; good arguments on a box without a GPU are E_NODEVICE (reported, not faked)."""
+    lib = _lib.load()
+    buf = (ctypes.c_uint8 * 64)()
+    ctr = (ctypes.c_int64 * 1)()
+    addr = ctypes.addressof(buf)
+    assert lib.vlmfw_dropout_keep_mask(addr, 4, 0, 0, 1, 0.3, None) == _lib.E_INVALID  # cols = 0
+    assert "dropout_keep_mask" in _lib.last_error()
+    assert lib.vlmfw_dropout_keep_mask(addr, 4, 16, 0, 1, 1.0, None) == _lib.E_INVALID  # p = 1 keeps nothing
+    assert lib.vlmfw_dropout_keep_mask(addr, 4, 16, -1, 1, 0.3, None) == _lib.E_INVALID  # negative global row
+    assert lib.vlmfw_dropout_keep_mask_dev(addr, 4, 16, 0, 1, None, 262, 0.3, None) == _lib.E_INVALID
+    assert "steps_done" in _lib.last_error()
+    assert lib.vlmfw_counter_add(None, 1, None) == _lib.E_INVALID
+    assert lib.vlmfw_probe_adamw_dev(addr, addr, addr, addr, 4, 5, None, 1e-4, 0.9, 0.999, 1e-8, 1e-4, None) == _lib.E_INVALID
+    assert lib.vlmfw_probe_bn_stats(None, 4, 16, addr, None) == _lib.E_INVALID
+    if not torch.cuda.is_available():
+        assert lib.vlmfw_dropout_keep_mask(addr, 4, 16, 0, 1, 0.3, None) == _lib.E_NODEVICE
+        assert lib.vlmfw_counter_add(ctypes.addressof(ctr), 1, None) == _lib.E_NODEVICE
+        assert ctr[0] == 0  # nothing ran on the host instead
