@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define VLMFW_ABI_VERSION 1
+#define VLMFW_ABI_VERSION 2
 
 enum {
     VLMFW_OK = 0,
@@ -41,7 +41,7 @@ enum {
     VLMFW_E_CUDA = -3,      /* a CUDA runtime / driver call failed */
     VLMFW_E_STATE = -4,     /* weights missing, workspace too small, ... */
     VLMFW_E_NOTFOUND = -5,  /* unknown weight name */
-    VLMFW_E_RANGE = -6      /* a weight does not fit the fp16 range: recreate the tower with VLMFW_CDT_BF16 */
+    VLMFW_E_RANGE = -6      /* a weight tensor holds a non-finite value (NaN / Inf) */
 };
 
 /* tower family: which HF vision transformer the adapter wrapped */
@@ -70,9 +70,12 @@ enum { VLMFW_DT_BF16 = 0, VLMFW_DT_F16 = 1, VLMFW_DT_F32 = 2 };
  *         (fp16 autocast, probing/test/base_tester.py:50). LayerNorm statistics, softmax and all accumulation stay fp32;
  *         the residual stream itself is kept in fp16 (it is at once the next GEMM's A operand; measured cost 3e-4 of
  *         logit error, gain 4.6 % of the step — VLMFW_RESIDUAL=32 in the environment keeps an fp32 stream);
- *         16-bit stores saturate to +-65504 instead of overflowing to inf.
- *   BF16: 8-bit mantissa, fp32 range, fp32 residual stream — for checkpoints whose weights exceed the fp16 range (set_weight reports
- *         VLMFW_E_RANGE and the host recreates the tower with this mode). */
+ *         16-bit stores saturate to +-65504 instead of overflowing to inf, and every clamped store is counted
+ *         (vlmfw_tower_saturation). A weight matrix whose largest entry exceeds the fp16 range is stored divided by a
+ *         power of two and its GEMM's accumulator multiplied back (exact), so the mode never depends on weight range.
+ *   BF16: 8-bit mantissa, fp32 range, fp32 residual stream. Weight rounding alone costs 1.5e-2 of probe-logit error: this
+ *         mode does NOT meet the 1e-2 logit tolerance (cosine >= 0.999 and the labels hold); it exists for A/B measurements
+ *         and for callers that ask for bf16 explicitly. */
 enum { VLMFW_CDT_F16 = 0, VLMFW_CDT_BF16 = 1 };
 /* GEMM epilogues (kernel-level entry point, used by the parity tests) */
 enum {
@@ -138,6 +141,16 @@ void vlmfw_tower_destroy(vlmfw_tower* t);
 int vlmfw_tower_set_weight(vlmfw_tower* t, const char* name, const float* src, int64_t numel, void* stream);
 /* 0 when every tensor the configuration needs has been set, else VLMFW_E_STATE (message names the first missing) */
 int vlmfw_tower_ready(vlmfw_tower* t);
+/* Load-time step after the last set_weight: builds the derived operands (LayerNorm folded into the QKV / fc1 matrices,
+ * position-embedding tables). Synchronises `stream` (it reads back one scalar per folded matrix to pick the fp16 operand
+ * scale), so call it outside CUDA-graph capture; vlmfw_tower_forward does it lazily when it has not been called. */
+int vlmfw_tower_prepare(vlmfw_tower* t, void* stream);
+/* Power-of-two scale the 16-bit operand of weight matrix `name` is stored divided by (1 unless max |W| > 32768). */
+int vlmfw_tower_weight_scale(const vlmfw_tower* t, const char* name, float* host_scale);
+/* fp16 towers: number of 16-bit activation stores (one thread's 32-column chunk of one row of the QKV / fc1 outputs or of
+ * the residual stream) in which at least one value was clamped to +-65504 since creation / the last reset. 0 means no
+ * forward clipped. Synchronises `stream`. bf16 towers always report 0 (fp32 exponent range). */
+int vlmfw_tower_saturation(vlmfw_tower* t, int64_t* host_count, int32_t reset, void* stream);
 size_t vlmfw_tower_workspace_bytes(const vlmfw_tower* t, int32_t batch);
 int32_t vlmfw_tower_tokens(const vlmfw_tower* t); /* S */
 /* pixels -> pooled features [B, D] fp32 (what VisionBackbone.forward returns) */
@@ -284,6 +297,8 @@ typedef struct vlmfw_gemm_desc {
     const float* bias; int32_t epi, act; void* out; int32_t ldo; const float* resid; int32_t ldr; int32_t block_n;
     const void* ln_stats; int32_t ln_np, ln_dim; float ln_eps;
     void* h16_out; int32_t ld_h16; void* stats_out;
+    float acc_scale;  /* accumulator scale (W holds W_true / acc_scale); 0 is read as 1 */
+    void* sat_count;  /* device uint64 counter of clamped fp16 stores, or NULL */
 } vlmfw_gemm_desc;
 int vlmfw_gemm_tn_ex(const vlmfw_gemm_desc* desc, void* stream);
 int32_t vlmfw_gemm_stats_parts(int32_t n, int32_t block_n);

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/vlmfw_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert _lib.load().vlmfw_abi_version() == 1
+    assert _lib.load().vlmfw_abi_version() == 2
 
 
 def test_no_device_is_reported_not_faked():

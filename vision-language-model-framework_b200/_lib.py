@@ -53,7 +53,7 @@ class GemmDesc(C.Structure):
         ("a", _vp), ("lda", _i32), ("w", _vp), ("ldw", _i32), ("dtype", _i32), ("m", _i32), ("n", _i32), ("k", _i32),
         ("bias", _vp), ("epi", _i32), ("act", _i32), ("out", _vp), ("ldo", _i32), ("resid", _vp), ("ldr", _i32),
         ("block_n", _i32), ("ln_stats", _vp), ("ln_np", _i32), ("ln_dim", _i32), ("ln_eps", _f32),
-        ("h16_out", _vp), ("ld_h16", _i32), ("stats_out", _vp),
+        ("h16_out", _vp), ("ld_h16", _i32), ("stats_out", _vp), ("acc_scale", _f32), ("sat_count", _vp),
     ]
 
 
@@ -66,6 +66,9 @@ SIGNATURES = {
     "vlmfw_tower_destroy": (None, [_vp]),
     "vlmfw_tower_set_weight": (C.c_int, [_vp, C.c_char_p, _vp, _i64, _vp]),
     "vlmfw_tower_ready": (C.c_int, [_vp]),
+    "vlmfw_tower_prepare": (C.c_int, [_vp, _vp]),
+    "vlmfw_tower_weight_scale": (C.c_int, [_vp, C.c_char_p, C.POINTER(_f32)]),
+    "vlmfw_tower_saturation": (C.c_int, [_vp, C.POINTER(_i64), _i32, _vp]),
     "vlmfw_tower_workspace_bytes": (_sz, [_vp, _i32]),
     "vlmfw_tower_tokens": (_i32, [_vp]),
     "vlmfw_tower_forward": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp]),

@@ -226,11 +226,8 @@ int launch_att(const void* qkv, int batch, int tokens, int heads, int dh, void* 
                int q_begin = 0) {
     using C = AttCfg<DHP>;
     auto kern = attention_kernel<DHP, F16>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VLMFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> smem_opt_in{0};  // per instantiation, one bit per device
+    VLMFW_CUDA_OK(ensure_dynamic_smem(kern, C::SMEM_BYTES, smem_opt_in));
     dim3 grid((tokens - q_begin + BQ - 1) / BQ, heads, batch);
     const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dh));
     kern<<<grid, ATT_THREADS, C::SMEM_BYTES, stream>>>(static_cast<const __nv_bfloat16*>(qkv),

@@ -211,7 +211,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         TR(0, 1);
                         mbar_wait(q_empty, (k & 1) ^ 1);
                         TR(0, 2);
-                        const bool ld = !(p.dbg & 128), ldt = C::TAIL && ld && !(p.dbg & 8);
+                        const bool ld = !VLMFW_DBG(p, 128), ldt = C::TAIL && ld && !VLMFW_DBG(p, 8);
                         mbar_arrive_expect_tx(q_full, (ld ? C::Q_MAIN : 0) + (ldt ? C::Q_BYTES - C::Q_MAIN : 0));
                         if (ld) tma_load_5d(sQ, &map_q, q_full, 0, h, 0, qb * QB, b);
                         if (ldt) tma_load_5d(sQ + C::Q_MAIN, &map_qt, q_full, 64, h, 0, qb * QB, b);
@@ -220,7 +220,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     TR(0, 3);
                     mbar_wait(&k_empty[st], ((s / C::NKV) & 1) ^ 1);
                     TR(0, 4);
-                    const bool ld = !(p.dbg & 64), ldt = C::TAIL && ld && !(p.dbg & 8);
+                    const bool ld = !VLMFW_DBG(p, 64), ldt = C::TAIL && ld && !VLMFW_DBG(p, 8);
                     mbar_arrive_expect_tx(&k_full[st], (ld ? C::KV_MAIN : 0) + (ldt ? C::KV_BYTES - C::KV_MAIN : 0));
                     if (ld) tma_load_5d(sK + st * C::KV_BYTES, &map_kv, &k_full[st], 0, h, 1, j * KB, b);
                     if (ldt) tma_load_5d(sK + st * C::KV_BYTES + C::KV_MAIN, &map_kvt, &k_full[st], 64, h, 1, j * KB, b);
@@ -232,7 +232,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     TR(0, 5);
                     mbar_wait(&v_empty[st], ((sv / C::NKV) & 1) ^ 1);
                     TR(0, 6);
-                    const bool ld = !(p.dbg & 16), ldt = C::TAIL && ld && !(p.dbg & 8);
+                    const bool ld = !VLMFW_DBG(p, 16), ldt = C::TAIL && ld && !VLMFW_DBG(p, 8);
                     mbar_arrive_expect_tx(&v_full[st], (ld ? C::KV_MAIN : 0) + (ldt ? C::KV_BYTES - C::KV_MAIN : 0));
                     if (ld) tma_load_5d(sV + st * C::KV_BYTES, &map_kv, &v_full[st], 0, h, 2, j * KB, b);
                     if (ldt) tma_load_5d(sV + st * C::KV_BYTES + C::KV_MAIN, &map_kvt, &v_full[st], 64, h, 2, j * KB, b);
@@ -270,7 +270,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 mbar_wait(&s_empty[sb], ((t >> 1) & 1) ^ 1);
                 TR(1, 4);
                 tc_fence_after();
-                if (!(p.dbg & 4)) {
+                if (!VLMFW_DBG(p, 4)) {
                     const uint32_t d = tmem_base + TM_S + sb * KB;
                     const uint32_t b0 = k_u32 + st * C::KV_BYTES;
                     const uint64_t ad = umma_desc_sw128(q_u32), bd = umma_desc_sw128(b0);
@@ -298,7 +298,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 if (j == 0) mbar_wait(o_empty, (k & 1) ^ 1);
                 TR(3, 8);
                 tc_fence_after();
-                if (!(p.dbg & 2)) {
+                if (!VLMFW_DBG(p, 2)) {
                     const uint32_t d = tmem_base + TM_O;
                     const uint32_t a0 = p_u32 + pb * C::P_BYTES, b0 = v_u32 + st * C::KV_BYTES;
                     const int ksteps = kcols_of(j) >> 4;  // 16 keys per step
@@ -461,7 +461,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 TR(2, 4);
                 mbar_wait(&p_empty[pb], ((t / NP) & 1) ^ 1);
                 TR(2, 5);
-                if (!(p.dbg & 1)) {
+                if (!VLMFW_DBG(p, 1)) {
                     float sum[4] = {0.f, 0.f, 0.f, 0.f};
                     const float neg_m = -m;
                     const uint32_t pdst = prow_u32 + pb * C::P_BYTES;
@@ -511,7 +511,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             tc_fence_before();  // O is in registers: hand the accumulator back to the MMA warp
             __syncwarp();
             if (lane == 0) mbar_arrive(o_empty);
-            if (warp_live_q && !(p.dbg & 32)) {
+            if (warp_live_q && !VLMFW_DBG(p, 32)) {
                 // O / l -> 16-bit -> this warp's staging slabs (its own 32 rows of the two P tiles, free once the item's
                 // last P·V has completed) -> two 16-row TMA stores into ctx[b, tok, h, :] (rows past S are clipped).
                 // Row-strided 16-byte global stores from registers cost ~2300 cycles per item here (timeline trace).
@@ -637,11 +637,8 @@ int launch_tc(const void* qkv, int batch, int tokens, int heads, void* out, int 
     int rc = get_maps<DH>(qkv, out, f16, batch, tokens, heads, &ms);
     if (rc != VLMFW_OK) return rc;
     auto kern = attention_tc_kernel<DH, F16>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VLMFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> smem_opt_in{0};  // per instantiation, one bit per device
+    VLMFW_CUDA_OK(ensure_dynamic_smem(kern, C::SMEM_BYTES, smem_opt_in));
     TcParams p;
     p.out = out;
     p.S = tokens;
@@ -653,10 +650,14 @@ int launch_tc(const void* qkv, int batch, int tokens, int heads, void* out, int 
     p.num_items = batch * heads * p.nq;
     p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(DH));
     p.f16 = f16 ? 1 : 0;
+#ifdef VLMFW_DEBUG_MASKS
     {
         const char* e = getenv("VLMFW_ATTN_DBG");
         p.dbg = e ? atoi(e) : 0;
     }
+#else
+    p.dbg = 0;
+#endif
     const int slots = 2 * num_sms();
     const int grid = p.num_items < slots ? p.num_items : slots;
     {

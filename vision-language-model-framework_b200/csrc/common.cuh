@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -39,6 +40,29 @@ int64_t& launch_counter();  // counts kernels launched by this library on the ca
         VLMFW_CUDA_OK(cudaGetLastError());     \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: one process may drive several
+// GPUs (TowerEngine(device=...)), so the opt-in is remembered per (kernel instantiation, device), not per process.
+// `done` is a bit mask over device ordinals (one static per kernel instantiation at the call site).
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kern, int bytes, std::atomic<uint64_t>& done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (static_cast<unsigned>(dev) & 63u);
+    if (dev < 64 && (done.load(std::memory_order_acquire) & bit)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev < 64) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
+// Bottleneck-experiment switches inside the hot kernels (VLMFW_GEMM_DBG / VLMFW_ATTN_DBG bit masks) exist only in
+// builds compiled with -DVLMFW_DEBUG_MASKS (tools/ variants); the shipped library folds them to `false`.
+#ifdef VLMFW_DEBUG_MASKS
+#define VLMFW_DBG(p, bit) (((p).dbg & (bit)) != 0)
+#else
+#define VLMFW_DBG(p, bit) false
+#endif
+
 struct GemmArgs {
     const void* a = nullptr;  // [M,K] bf16
     int lda = 0;
@@ -67,6 +91,11 @@ struct GemmArgs {
     int ld_h16 = 0;
     void* stats_out = nullptr;
     bool f16 = false;  // 16-bit format of A, W and the 16-bit output: false = bf16, true = fp16 (A and W must agree)
+    // the accumulator is multiplied by acc_scale before bias / residual / LayerNorm scaling: W holds W_true / acc_scale
+    // when W_true does not fit the fp16 range (tower.cu picks a power of two)
+    float acc_scale = 1.f;
+    // fp16 outputs only: device counter of (row, chunk) stores that clamped at +-65504 (NULL = not counted)
+    unsigned long long* sat_count = nullptr;
 };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda). dims[0] / box[0] = innermost.
@@ -85,10 +114,13 @@ int launch_layernorm(const float* x, int rows, int dim, const float* gamma, cons
                      int out_dtype, cudaStream_t stream);
 // fp32 rows -> plain 16-bit cast + (sum, sum of squares) in partial slot 0 of stats [rows][np] float2 (others zeroed)
 int launch_row_stats_cast(const float* x, int rows, int dim, void* out16, bool f16, void* stats, int np,
-                          cudaStream_t stream);
+                          cudaStream_t stream, unsigned long long* sat = nullptr);
 // W'[n,k] = round16(gamma[k] W[n,k] - mean_j(gamma[j] W[n,j])) (row stride ld), c2[n] = sum_k beta[k] W[n,k] + bias[n]
+// inv_scale multiplies the folded values before rounding (1 / acc_scale of the consuming GEMM); amax_bits (device, may be
+// NULL) receives max |unscaled folded value| as a float bit pattern through atomicMax (zero it first)
 int launch_ln_fold_weight(const float* w, int n, int k, const float* gamma, const float* beta, const float* bias,
-                          void* w16, int ld, bool f16, float* c2, cudaStream_t stream);
+                          void* w16, int ld, bool f16, float* c2, cudaStream_t stream, float inv_scale = 1.f,
+                          unsigned int* amax_bits = nullptr);
 int launch_attention(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out,
                      cudaStream_t stream);
 // tcgen05 attention (attention_tc.cu): 0 = launched, 1 = shape not covered (use launch_attention's generic kernel), <0 = error
@@ -103,7 +135,10 @@ int launch_pool(const float* h, int batch, int tokens, int dim, int pool, const 
 // same, reading a 16-bit (VLMFW_DT_F16 / VLMFW_DT_BF16) or fp32 hidden state
 int launch_pool_dt(const void* h, int in_dt, int batch, int tokens, int dim, int pool, const float* gamma,
                    const float* beta, float eps, float* pooled, cudaStream_t stream);
-int launch_pack_16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, bool f16, cudaStream_t stream);
+int launch_pack_16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, bool f16, cudaStream_t stream,
+                   float inv_scale = 1.f);
+// power-of-two scale s >= 1 with amax / s <= 32768: what a weight matrix is divided by so that it fits fp16
+float fp16_weight_scale(float amax);
 // max |x| over a device fp32 array, returned to the host (synchronises `stream`; load-time only)
 int device_absmax(const float* src, int64_t numel, float* host_out, cudaStream_t stream);
 int launch_add_rows(const float* a, const float* b, float* out, int64_t rows, int64_t cols, int64_t a_row0,

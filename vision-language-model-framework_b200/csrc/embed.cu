@@ -74,12 +74,12 @@ __global__ void fill_cls_kernel(const float* __restrict__ cls_pos0, float* __res
 
 template <bool F16>
 __global__ void pack_16_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, uint16_t* dst,
-                               int64_t dst_ld) {
+                               int64_t dst_ld, float inv_scale) {
     const int64_t total = rows * dst_ld;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t r = i / dst_ld, c = i - r * dst_ld;
-        const float v = c < cols ? src[r * cols + c] : 0.f;
+        const float v = c < cols ? src[r * cols + c] * inv_scale : 0.f;  // inv_scale: power of two (exact) or 1
         if constexpr (F16) dst[i] = __half_as_ushort(__float2half_rn(v));
         else dst[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
     }
@@ -154,15 +154,24 @@ int launch_fill_cls(const float* cls_pos0, float* h, int batch, int tokens, int 
     return VLMFW_OK;
 }
 
-int launch_pack_16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, bool f16, cudaStream_t stream) {
+int launch_pack_16(const float* src, int64_t rows, int64_t cols, void* dst, int64_t dst_ld, bool f16, cudaStream_t stream,
+                   float inv_scale) {
     VLMFW_REQUIRE(src && dst && rows > 0 && cols > 0 && dst_ld >= cols, "pack_16: bad arguments");
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
     const int grid = grid_for(static_cast<size_t>(rows * dst_ld), 256);
-    if (f16) pack_16_kernel<true><<<grid, 256, 0, stream>>>(src, rows, cols, static_cast<uint16_t*>(dst), dst_ld);
-    else pack_16_kernel<false><<<grid, 256, 0, stream>>>(src, rows, cols, static_cast<uint16_t*>(dst), dst_ld);
+    if (f16) pack_16_kernel<true><<<grid, 256, 0, stream>>>(src, rows, cols, static_cast<uint16_t*>(dst), dst_ld, inv_scale);
+    else pack_16_kernel<false><<<grid, 256, 0, stream>>>(src, rows, cols, static_cast<uint16_t*>(dst), dst_ld, inv_scale);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
+}
+
+// Power-of-two scale s >= 1 with amax / s <= 32768 (half the fp16 range: headroom for the rounding of the LayerNorm
+// fold). The 16-bit operand then holds W / s exactly-scaled and the GEMM epilogue multiplies the accumulator by s.
+float fp16_weight_scale(float amax) {
+    float s = 1.f;
+    while (amax / s > 32768.f && s < 1.0e30f) s *= 2.f;
+    return s;
 }
 
 int device_absmax(const float* src, int64_t numel, float* host_out, cudaStream_t stream) {

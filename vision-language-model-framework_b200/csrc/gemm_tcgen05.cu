@@ -99,6 +99,12 @@ struct KParams {
     float2* stats_out;
     int stats_np;
     int h16_on;
+    // scale of the accumulator: the 16-bit W operand holds W / acc_scale when a weight exceeded the fp16 range
+    // (power of two, so the product is exact); 1 otherwise
+    float acc_scale;
+    // fp16 outputs saturate to +-65504 (cvt.rn.satfinite) instead of overflowing; *sat counts the (row, chunk) stores in
+    // which at least one value was clamped, so the host can tell that a forward clipped (NULL: not counted)
+    unsigned long long* sat;
     int dbg;  // VLMFW_GEMM_DBG bit mask (bottleneck experiments only): 1 no TMA after the ring is primed, 2 no epilogue
               // global traffic, 4 no MMA issue
 };
@@ -207,7 +213,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
                     uint8_t* sb = sa + C::A_BYTES;
-                    if ((p.dbg & 1) && (tile != worker || kb >= C::STAGES)) {
+                    if (VLMFW_DBG(p, 1) && (tile != worker || kb >= C::STAGES)) {
                         if (cta_rank == 0) mbar_arrive(&full_bar[stage]);
                     } else if constexpr (CG == 2) {
                         // both CTAs load into their own smem; all bytes are counted on the LEADER's full barrier
@@ -248,7 +254,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint64_t bdesc = umma_desc_sw128(sa + C::A_BYTES);
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                        if (p.dbg & 4) break;
+                        if (VLMFW_DBG(p, 4)) break;
                         // advancing K inside the 128B swizzle row: +32 bytes -> +2 in the (addr >> 4) field
                         if constexpr (CG == 2)
                             umma_bf16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(ks * 2),
@@ -326,6 +332,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     mu = s1 * p.ln_inv_dim;
                     rstd = rsqrtf(fmaxf(s2 * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
                 }
+                rstd *= p.acc_scale;
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 uint32_t v[32];
@@ -350,13 +357,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 32; ++j) y[j] = activation<ACT>(y[j]);
                     if (p.out_f16) {
+                        if (p.sat != nullptr) {  // warp-uniform
+                            float amax = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) amax = fmaxf(amax, fmaxf(fabsf(y[j]), fabsf(y[j + 1])));
+                            if (amax > 65504.f) atomicAdd(p.sat, 1ull);
+                        }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) o[j] = pack_f16x2(y[2 * j], y[2 * j + 1]);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(y[2 * j], y[2 * j + 1]);
                     }
-                    if (p.dbg & 2) continue;
+                    if (VLMFW_DBG(p, 2)) continue;
                     const uint32_t box = row_u32 + (q & 1u) * 2048u;
                     if (lane == 0) tma_store_wait_read<1>();  // the store issued two chunks ago has left this box
                     __syncwarp();
@@ -398,7 +411,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 mbar_arrive_expect_tx(&my_bar[b], BOX);
                 tma_load_2d(stg + b * BOX, &tmap_res, &my_bar[b], cx, cy);
             };
-            if (lane == 0 && !(p.dbg & 2)) {
+            if (lane == 0 && !VLMFW_DBG(p, 2)) {
                 for (uint32_t qq = 0; qq < RES_NBUF - 1 && qq < total_q; ++qq) issue_load(qq);
             }
             auto unpack2 = [&](uint32_t u, float& lo, float& hi) {
@@ -420,7 +433,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < RCHUNKS; ++c, ++q) {
-                    if (p.dbg & 2) continue;
+                    if (VLMFW_DBG(p, 2)) continue;
                     const int nc = n0 + c * RC;
                     uint32_t v[RC];
                     tmem_ld_32x32(lane_taddr + static_cast<uint32_t>(acc * BN + c * RC), v);
@@ -431,6 +444,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     // warp-uniform: columns a narrow last tile never wrote (its MMA is as wide as N rounded up to 16) hold
                     // stale TMEM and must not reach the statistics
                     const int n16 = (p.n + 15) & ~15;
+                    float amax = 0.f;  // largest |value| this thread stores in this chunk (fp16 saturation report)
 #pragma unroll
                     for (int g16 = 0; g16 < RC / 16; ++g16) {
                         if (nc + 16 * g16 >= n16) {
@@ -456,8 +470,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         for (int i = 0; i < 4; ++i) {
                             float lo, hi;
                             unpack2(u[i], lo, hi);
-                            lo += __uint_as_float(v[8 * j + 2 * i]) + bv[2 * i];
-                            hi += __uint_as_float(v[8 * j + 2 * i + 1]) + bv[2 * i + 1];
+                            lo += fmaf(__uint_as_float(v[8 * j + 2 * i]), p.acc_scale, bv[2 * i]);
+                            hi += fmaf(__uint_as_float(v[8 * j + 2 * i + 1]), p.acc_scale, bv[2 * i + 1]);
+                            amax = fmaxf(amax, fmaxf(fabsf(lo), fabsf(hi)));
                             u[i] = p.out_f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
                             unpack2(u[i], lo, hi);  // statistics of what is stored
                             s1 += lo + hi;
@@ -467,6 +482,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                      "r"(u[3])
                                      : "memory");
                     }
+                    if (p.out_f16 && p.sat != nullptr && amax > 65504.f) atomicAdd(p.sat, 1ull);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -478,7 +494,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     __syncwarp();
                 }
-                if (p.stats_out != nullptr && m0 + lane < p.m && !(p.dbg & 2)) {
+                if (p.stats_out != nullptr && m0 + lane < p.m && !VLMFW_DBG(p, 2)) {
                     p.stats_out[static_cast<size_t>(m0 + lane) * p.stats_np + (tile % n_tiles) * 2 + half] =
                         make_float2(s1, s2);
                 }
@@ -509,7 +525,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 mbar_arrive_expect_tx(&my_bar[b], RES_BOX_BYTES);
                 tma_load_2d(stg + b * RES_BOX_BYTES, &tmap_res, &my_bar[b], cx, cy);
             };
-            if (lane == 0 && !(p.dbg & 2)) {
+            if (lane == 0 && !VLMFW_DBG(p, 2)) {
                 for (uint32_t qq = 0; qq < RES_NBUF - 1 && qq < total_q; ++qq) issue_load(qq);
             }
             static_assert(RES_NBUF >= 3, "ring: chunk q's store may still read its box while q + 1 is processed");
@@ -522,7 +538,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < RCHUNKS; ++c, ++q) {
-                    if (p.dbg & 2) continue;
+                    if (VLMFW_DBG(p, 2)) continue;
                     const int nc = n0 + c * RES_COLS;
                     uint32_t v[RES_COLS];
                     tmem_ld_row(lane_taddr + static_cast<uint32_t>(acc * BN + c * RES_COLS), v);
@@ -545,10 +561,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                                      : "r"(a));
-                        r.x += __uint_as_float(v[4 * j + 0]) + bv.x;
-                        r.y += __uint_as_float(v[4 * j + 1]) + bv.y;
-                        r.z += __uint_as_float(v[4 * j + 2]) + bv.z;
-                        r.w += __uint_as_float(v[4 * j + 3]) + bv.w;
+                        r.x += fmaf(__uint_as_float(v[4 * j + 0]), p.acc_scale, bv.x);
+                        r.y += fmaf(__uint_as_float(v[4 * j + 1]), p.acc_scale, bv.y);
+                        r.z += fmaf(__uint_as_float(v[4 * j + 2]), p.acc_scale, bv.z);
+                        r.w += fmaf(__uint_as_float(v[4 * j + 3]), p.acc_scale, bv.w);
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(r.x), "f"(r.y), "f"(r.z),
                                      "f"(r.w)
                                      : "memory");
@@ -585,7 +601,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     __syncwarp();
                 }
-                if (p.stats_out != nullptr && m0 + lane < p.m && !(p.dbg & 2)) {
+                if (p.stats_out != nullptr && m0 + lane < p.m && !VLMFW_DBG(p, 2)) {
                     p.stats_out[static_cast<size_t>(m0 + lane) * p.stats_np + (tile % n_tiles) * 2 + half] =
                         make_float2(s1, s2);
                 }
@@ -602,7 +618,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         float4 rnext[8];
         auto resid_issue = [&](int tile, int c, float4 (&r)[8]) {
             if constexpr (EPI == VLMFW_EPI_BIAS_RESID_F32) {
-                if (p.dbg & 2) return;
+                if (VLMFW_DBG(p, 2)) return;
                 const int m0 = (tile / n_tiles) * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
                 const int col = (tile % n_tiles) * BN + half * COLS_PER_WARP + c * 32 + cj * 4;
 #pragma unroll
@@ -634,7 +650,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (c + 1 < CHUNKS) resid_issue(tile, c + 1, rnext);
                     else if (tile + num_workers < num_tiles) resid_issue(tile + num_workers, 0, rnext);
                 }
-                if (nc >= p.n || (p.dbg & 2)) continue;  // warp-uniform: whole chunk is past the N edge (prefetch above still ran)
+                if (nc >= p.n || VLMFW_DBG(p, 2)) continue;  // warp-uniform: whole chunk is past the N edge (prefetch above still ran)
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                        static_cast<uint32_t>(acc * BN + half * COLS_PER_WARP + c * 32);
@@ -663,10 +679,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
                                  : "r"(src));
                     if (row < p.m && col_ok) {
-                        a.x += bv.x;
-                        a.y += bv.y;
-                        a.z += bv.z;
-                        a.w += bv.w;
+                        a.x = fmaf(a.x, p.acc_scale, bv.x);
+                        a.y = fmaf(a.y, p.acc_scale, bv.y);
+                        a.z = fmaf(a.z, p.acc_scale, bv.z);
+                        a.w = fmaf(a.w, p.acc_scale, bv.w);
                         int orow = row;
                         if (p.grp > 0) orow = (row / p.grp) * p.grp_out + (row % p.grp) + p.grp_off;
                         if constexpr (EPI == VLMFW_EPI_BIAS_RESID_F32) {
@@ -831,11 +847,8 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
         }
     }
     auto kern = gemm_bf16_tn_kernel<BN, EPI, ACT, CG, GEN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VLMFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> smem_opt_in{0};  // per instantiation, one bit per device
+    VLMFW_CUDA_OK(ensure_dynamic_smem(kern, C::SMEM_BYTES, smem_opt_in));
     KParams p;
     p.m = g.m;
     p.n = g.n;
@@ -860,11 +873,17 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
     p.stats_out = reinterpret_cast<float2*>(g.stats_out);
     p.stats_np = 2 * ((g.n + BN - 1) / BN);
     p.h16_on = g.h16_out != nullptr ? 1 : 0;
+    p.acc_scale = g.acc_scale > 0.f ? g.acc_scale : 1.f;
+    p.sat = g.sat_count;
+#ifdef VLMFW_DEBUG_MASKS
     static const int dbg = []() {
         const char* e = getenv("VLMFW_GEMM_DBG");
         return e ? atoi(e) : 0;
     }();
     p.dbg = dbg;
+#else
+    p.dbg = 0;
+#endif
     constexpr int TILE_M = BM * CG;
     const int m_tiles = (g.m + TILE_M - 1) / TILE_M;
     const int n_tiles = (g.n + BN - 1) / BN;

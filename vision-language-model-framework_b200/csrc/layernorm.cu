@@ -244,19 +244,20 @@ __global__ void __launch_bounds__(128) pool_cls_ln2_kernel(const void* __restric
 template <bool F16>
 __global__ void __launch_bounds__(256) row_stats_cast_kernel(const float* __restrict__ x, int rows, int dim,
                                                              void* __restrict__ out16, float2* __restrict__ stats,
-                                                             int np) {
+                                                             int np, unsigned long long* __restrict__ sat) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
     const int nchunks = dim >> 2;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * dim);
     uint2* orow = reinterpret_cast<uint2*>(static_cast<uint16_t*>(out16) + static_cast<size_t>(warp) * dim);
-    float s1 = 0.f, s2 = 0.f;
+    float s1 = 0.f, s2 = 0.f, amax = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
         const int c = i * 32 + lane;
         if (c < nchunks) {
             const float4 v = xr[c];
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
             s1 += (v.x + v.y) + (v.z + v.w);
             s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
             uint2 o;
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(256) row_stats_cast_kernel(const float* __rest
             orow[c] = o;
         }
     }
+    if (F16 && sat != nullptr && amax > 65504.f) atomicAdd(sat, 1ull);  // the fp16 cast above clamped (satfinite)
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
     if (lane < np) stats[static_cast<size_t>(warp) * np + lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
@@ -279,7 +281,8 @@ __global__ void __launch_bounds__(256) row_stats_cast_kernel(const float* __rest
 template <bool F16>
 __global__ void __launch_bounds__(256) ln_fold_weight_kernel(const float* __restrict__ w, int k, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const float* __restrict__ bias,
-                                                             uint16_t* __restrict__ w16, int ld, float* __restrict__ c2) {
+                                                             uint16_t* __restrict__ w16, int ld, float* __restrict__ c2,
+                                                             float inv_scale, unsigned int* __restrict__ amax_bits) {
     const int n = blockIdx.x;
     const float* wr = w + static_cast<size_t>(n) * k;
     uint16_t* orow = w16 + static_cast<size_t>(n) * ld;
@@ -312,43 +315,54 @@ __global__ void __launch_bounds__(256) ln_fold_weight_kernel(const float* __rest
     }
     __syncthreads();
     const float mean = row_mean;
+    unsigned int am = 0;  // max |folded value| of this thread as a bit pattern (orders like the float; NaN / Inf on top)
     for (int i = threadIdx.x; i < ld; i += blockDim.x) {
         uint16_t bits = 0;
         if (i < k) {
             const float wf = fmaf(wr[i], gamma[i], -mean);
-            if constexpr (F16) bits = __half_as_ushort(__float2half_rn(wf));
-            else bits = __bfloat16_as_ushort(__float2bfloat16_rn(wf));
+            am = max(am, __float_as_uint(wf) & 0x7FFFFFFFu);
+            const float ws = wf * inv_scale;  // power of two (exact) or 1
+            if constexpr (F16) bits = __half_as_ushort(__float2half_rn(ws));
+            else bits = __bfloat16_as_ushort(__float2bfloat16_rn(ws));
         }
         orow[i] = bits;
+    }
+    if (amax_bits != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) am = max(am, __shfl_xor_sync(0xffffffffu, am, o));
+        if ((threadIdx.x & 31) == 0 && am != 0) atomicMax(amax_bits, am);
     }
 }
 
 }  // namespace
 
 int launch_row_stats_cast(const float* x, int rows, int dim, void* out16, bool f16, void* stats, int np,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, unsigned long long* sat) {
     VLMFW_REQUIRE(x && out16 && stats, "row_stats_cast: null pointer");
     VLMFW_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAX_CHUNKS * 128, "row_stats_cast: bad dim %d", dim);
     VLMFW_REQUIRE(np >= 1 && np <= 32, "row_stats_cast: %d partial slots (1..32)", np);
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
     const int grid = (rows + 7) / 8;
-    if (f16) row_stats_cast_kernel<true><<<grid, 256, 0, stream>>>(x, rows, dim, out16, static_cast<float2*>(stats), np);
-    else row_stats_cast_kernel<false><<<grid, 256, 0, stream>>>(x, rows, dim, out16, static_cast<float2*>(stats), np);
+    if (f16) row_stats_cast_kernel<true><<<grid, 256, 0, stream>>>(x, rows, dim, out16, static_cast<float2*>(stats), np, sat);
+    else row_stats_cast_kernel<false><<<grid, 256, 0, stream>>>(x, rows, dim, out16, static_cast<float2*>(stats), np, sat);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
 
 int launch_ln_fold_weight(const float* w, int n, int k, const float* gamma, const float* beta, const float* bias,
-                          void* w16, int ld, bool f16, float* c2, cudaStream_t stream) {
+                          void* w16, int ld, bool f16, float* c2, cudaStream_t stream, float inv_scale,
+                          unsigned int* amax_bits) {
     VLMFW_REQUIRE(w && gamma && beta && w16 && c2, "ln_fold_weight: null pointer");
     VLMFW_REQUIRE(n > 0 && k > 0 && ld >= k, "ln_fold_weight: bad shape n=%d k=%d ld=%d", n, k, ld);
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
     if (f16)
-        ln_fold_weight_kernel<true><<<n, 256, 0, stream>>>(w, k, gamma, beta, bias, static_cast<uint16_t*>(w16), ld, c2);
+        ln_fold_weight_kernel<true><<<n, 256, 0, stream>>>(w, k, gamma, beta, bias, static_cast<uint16_t*>(w16), ld, c2,
+                                                           inv_scale, amax_bits);
     else
-        ln_fold_weight_kernel<false><<<n, 256, 0, stream>>>(w, k, gamma, beta, bias, static_cast<uint16_t*>(w16), ld, c2);
+        ln_fold_weight_kernel<false><<<n, 256, 0, stream>>>(w, k, gamma, beta, bias, static_cast<uint16_t*>(w16), ld, c2,
+                                                            inv_scale, amax_bits);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }

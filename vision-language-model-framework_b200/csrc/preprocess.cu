@@ -438,10 +438,9 @@ extern "C" int vlmfw_preproc_run(vlmfw_preproc* p, const uint8_t* packed, int64_
     const int in_stride = static_cast<int>(align16(static_cast<size_t>(plan.max_w) * 3 + 32));
     const size_t smem = static_cast<size_t>(kRowsPerCta) * in_stride + static_cast<size_t>(kRowsPerCta) * align16(static_cast<size_t>(S) * 3);
     VLMFW_REQUIRE(smem <= 220 * 1024, "preproc_run: image width %d needs %zu bytes of shared memory", plan.max_w, smem);
-    static thread_local size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        VLMFW_CUDA_OK(cudaFuncSetAttribute(resize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        smem_set = 220 * 1024;
+    if (smem > 48 * 1024) {
+        static std::atomic<uint64_t> rows_opt_in{0};  // one bit per device
+        VLMFW_CUDA_OK(ensure_dynamic_smem(resize_rows_kernel, 220 * 1024, rows_opt_in));
     }
     const int64_t before = launch_counter();
     dim3 g1((plan.max_rows + kRowsPerCta - 1) / kRowsPerCta, batch);

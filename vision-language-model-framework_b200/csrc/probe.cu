@@ -416,9 +416,8 @@ extern "C" int vlmfw_probe_linear_grads(const float* x, const int64_t* targets, 
     VLMFW_LAUNCH_CHECK();
     const size_t bwd_smem = (((static_cast<size_t>(batch) * classes + 31) & ~static_cast<size_t>(31)) +
                              static_cast<size_t>(BWD_WARPS) * (classes + 2) * 32) * sizeof(float);
-    static const cudaError_t bwd_attr = cudaFuncSetAttribute(probe_train_bwd_kernel,
-                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    VLMFW_CUDA_OK(bwd_attr);
+    static std::atomic<uint64_t> bwd_opt_in{0};  // one bit per device
+    VLMFW_CUDA_OK(ensure_dynamic_smem(probe_train_bwd_kernel, 96 * 1024, bwd_opt_in));
     probe_train_bwd_kernel<<<(dim + 31) / 32, 32 * BWD_WARPS, bwd_smem, s>>>(a);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;

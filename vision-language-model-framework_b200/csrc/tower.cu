@@ -16,6 +16,7 @@
 //   mid  16b  [M, I]    GELU(fc1) = A operand of fc2; the patch-gather matrix [B*P, 592] aliases it before layer 0
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -44,34 +45,49 @@ struct DevInfo {
     int sms = 0;
     char msg[256] = "";
 };
+// One record per device ordinal: a process may drive several GPUs (one TowerEngine per device), and both the
+// architecture check and the SM count belong to the CURRENT device of the calling thread.
+constexpr int kMaxDevices = 64;
+DevInfo probe_device(int dev) {
+    DevInfo d;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+        snprintf(d.msg, sizeof(d.msg), "cudaGetDeviceProperties(%d) failed", dev);
+        cudaGetLastError();
+        return d;
+    }
+    if (p.major != 10) {
+        snprintf(d.msg, sizeof(d.msg), "device %d (%.160s) is sm_%d%d; vlmfw_b200 kernels are sm_100a only", dev, p.name,
+                 p.major, p.minor);
+        return d;
+    }
+    d.rc = VLMFW_OK;
+    d.sms = p.multiProcessorCount;
+    return d;
+}
 const DevInfo& dev_info() {
-    static DevInfo info = []() {
+    static DevInfo none = []() {
         DevInfo d;
-        int n = 0;
-        cudaError_t e = cudaGetDeviceCount(&n);
-        if (e != cudaSuccess || n == 0) {
-            snprintf(d.msg, sizeof(d.msg), "no CUDA device (%s); vlmfw_b200 has no CPU fallback",
-                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
-            cudaGetLastError();
-            return d;
-        }
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
-            snprintf(d.msg, sizeof(d.msg), "cudaGetDeviceProperties failed");
-            return d;
-        }
-        if (p.major != 10) {
-            snprintf(d.msg, sizeof(d.msg), "device %.160s is sm_%d%d; vlmfw_b200 kernels are sm_100a only", p.name, p.major,
-                     p.minor);
-            return d;
-        }
-        d.rc = VLMFW_OK;
-        d.sms = p.multiProcessorCount;
+        snprintf(d.msg, sizeof(d.msg), "no CUDA device; vlmfw_b200 has no CPU fallback");
         return d;
     }();
-    return info;
+    static DevInfo table[kMaxDevices];
+    static std::once_flag once[kMaxDevices];
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        snprintf(none.msg, sizeof(none.msg), "no CUDA device (%s); vlmfw_b200 has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        cudaGetLastError();
+        return none;
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        cudaGetLastError();
+        return none;
+    }
+    std::call_once(once[dev], [dev]() { table[dev] = probe_device(dev); });
+    return table[dev];
 }
 }  // namespace
 
@@ -95,6 +111,7 @@ struct Slot {
     float** master = nullptr;  // matrices a LayerNorm is folded into keep their fp32 values: the 16-bit operand is
                                // rebuilt from (W, gamma, beta, bias) whenever any of them changes (build_derived)
     bool matrix = false;  // repack to fp16 / bf16 [rows, ld]
+    float* scale = nullptr;  // matrices: where the power-of-two operand scale of this matrix lives (acc_scale of its GEMM)
     int64_t rows = 0, cols = 0, ld = 0;
     bool required = true;
     bool set = false;
@@ -106,6 +123,9 @@ struct LayerW {
     void *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;  // wqkv / w1 hold gamma-folded weights
     float *wqkv32 = nullptr, *w132 = nullptr;                           // fp32 masters of the folded matrices
     float *c2qkv = nullptr, *c2fc1 = nullptr;  // derived: beta W^T + b (ln_fold_weight_kernel)
+    // fp16 towers: the 16-bit operand holds W / s (s a power of two, 1 unless max |W| exceeds the fp16 range) and the GEMM
+    // epilogue multiplies its accumulator by s — a weight beyond +-65504 no longer forces the whole tower into bf16
+    float s_qkv = 1.f, s_o = 1.f, s_fc1 = 1.f, s_fc2 = 1.f;
 };
 
 }  // namespace
@@ -115,6 +135,9 @@ struct vlmfw_tower {
     int P = 0, S = 0, D = 0, H = 0, dh = 0, I = 0, L = 0, kreal = 0, kpad = 0;
     std::vector<LayerW> layers;
     void* patch_w = nullptr;  // 16-bit [D, kpad]
+    float s_patch = 1.f;
+    unsigned long long* sat_dev = nullptr;  // fp16 towers: device counter of clamped 16-bit stores (see vlmfw_tower_saturation)
+    unsigned int* amax_dev = nullptr;       // load-time scratch of build_derived
     bool f16 = true;  // cfg.compute_dtype == VLMFW_CDT_F16
     // fp16 towers keep the residual stream itself in fp16 (xn is the stream): half the HBM traffic of the
     // out-proj / fc2 epilogues, which put out-proj on the HBM roofline with an fp32 stream. bf16 towers (8-bit mantissa)
@@ -139,10 +162,11 @@ struct vlmfw_tower {
     size_t host_pooled_bytes = 0;
 
     void add_slot(const std::string& name, void** dst, bool matrix, int64_t rows, int64_t cols, int64_t ld,
-                  bool required = true, float** master = nullptr) {
+                  bool required = true, float** master = nullptr, float* scale = nullptr) {
         Slot s;
         s.dst = dst;
         s.master = master;
+        s.scale = scale;
         s.matrix = matrix;
         s.rows = rows;
         s.cols = cols;
@@ -214,7 +238,7 @@ extern "C" int vlmfw_tower_create(const vlmfw_tower_cfg* cfg, vlmfw_tower** out)
     t->kpad = static_cast<int>(align_up(t->kreal, 64));
     t->layers.resize(t->L);
     const int64_t D = t->D, I = t->I;
-    t->add_slot("patch.w", &t->patch_w, true, D, t->kreal, t->kpad);
+    t->add_slot("patch.w", &t->patch_w, true, D, t->kreal, t->kpad, true, nullptr, &t->s_patch);
     t->add_slot("patch.b", reinterpret_cast<void**>(&t->patch_b), false, 1, D, D, cfg->conv_bias != 0);
     t->add_slot("cls", reinterpret_cast<void**>(&t->cls), false, 1, D, D, cfg->has_cls != 0);
     t->add_slot("pos", reinterpret_cast<void**>(&t->pos), false, t->S, D, D);
@@ -228,16 +252,23 @@ extern "C" int vlmfw_tower_create(const vlmfw_tower_cfg* cfg, vlmfw_tower** out)
         const std::string p = "L" + std::to_string(i) + ".";
         t->add_slot(p + "ln1.w", reinterpret_cast<void**>(&w.ln1w), false, 1, D, D);
         t->add_slot(p + "ln1.b", reinterpret_cast<void**>(&w.ln1b), false, 1, D, D);
-        t->add_slot(p + "qkv.w", &w.wqkv, true, 3 * D, D, D, true, &w.wqkv32);
+        t->add_slot(p + "qkv.w", &w.wqkv, true, 3 * D, D, D, true, &w.wqkv32, &w.s_qkv);
         t->add_slot(p + "qkv.b", reinterpret_cast<void**>(&w.bqkv), false, 1, 3 * D, 3 * D);
-        t->add_slot(p + "o.w", &w.wo, true, D, D, D);
+        t->add_slot(p + "o.w", &w.wo, true, D, D, D, true, nullptr, &w.s_o);
         t->add_slot(p + "o.b", reinterpret_cast<void**>(&w.bo), false, 1, D, D);
         t->add_slot(p + "ln2.w", reinterpret_cast<void**>(&w.ln2w), false, 1, D, D);
         t->add_slot(p + "ln2.b", reinterpret_cast<void**>(&w.ln2b), false, 1, D, D);
-        t->add_slot(p + "fc1.w", &w.w1, true, I, D, D, true, &w.w132);
+        t->add_slot(p + "fc1.w", &w.w1, true, I, D, D, true, &w.w132, &w.s_fc1);
         t->add_slot(p + "fc1.b", reinterpret_cast<void**>(&w.b1), false, 1, I, I);
-        t->add_slot(p + "fc2.w", &w.w2, true, D, I, t->Ild());
+        t->add_slot(p + "fc2.w", &w.w2, true, D, I, t->Ild(), true, nullptr, &w.s_fc2);
         t->add_slot(p + "fc2.b", reinterpret_cast<void**>(&w.b2), false, 1, D, D);
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&t->sat_dev), sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&t->amax_dev), sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(t->sat_dev, 0, sizeof(unsigned long long)) != cudaSuccess) {
+        set_error("tower_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        vlmfw_tower_destroy(t);
+        return VLMFW_E_CUDA;
     }
     *out = t;
     return VLMFW_OK;
@@ -252,6 +283,8 @@ extern "C" void vlmfw_tower_destroy(vlmfw_tower* t) {
     for (auto& w : t->layers)
         for (float* ptr : {w.c2qkv, w.c2fc1})
             if (ptr) cudaFree(ptr);
+    if (t->sat_dev) cudaFree(t->sat_dev);
+    if (t->amax_dev) cudaFree(t->amax_dev);
     if (t->posb) cudaFree(t->posb);
     if (t->cls_pos0) cudaFree(t->cls_pos0);
     if (t->host_pix_dev) cudaFree(t->host_pix_dev);
@@ -277,22 +310,22 @@ extern "C" int vlmfw_tower_set_weight(vlmfw_tower* t, const char* name, const fl
         VLMFW_CUDA_OK(cudaMalloc(s.dst, bytes));
     }
     if (s.matrix) {
-        if (t->f16) {
-            float amax = 0.f;
-            int rc = device_absmax(src, numel, &amax, st);
-            if (rc != VLMFW_OK) return rc;
-            if (!(amax < 6.0e4f)) {  // also catches NaN / Inf (bit pattern above any finite value)
-                set_error("tower_set_weight: '%s' has max |w| = %g, outside the fp16 range; recreate the tower with "
-                          "compute_dtype = VLMFW_CDT_BF16", name, static_cast<double>(amax));
-                return VLMFW_E_RANGE;
-            }
+        float amax = 0.f;
+        int rc = device_absmax(src, numel, &amax, st);
+        if (rc != VLMFW_OK) return rc;
+        if (!(amax < 3.0e38f)) {  // NaN / Inf: bit pattern above any finite value
+            set_error("tower_set_weight: '%s' holds a non-finite value", name);
+            return VLMFW_E_RANGE;
         }
         if (s.master != nullptr) {
-            // LayerNorm-folded matrix: keep the fp32 values; build_derived() writes the 16-bit operand
+            // LayerNorm-folded matrix: keep the fp32 values; build_derived() writes the 16-bit operand (and picks its scale
+            // from the FOLDED values gamma . W - rowmean, which are what is rounded to 16 bits)
             if (*s.master == nullptr) VLMFW_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(s.master), static_cast<size_t>(numel) * 4));
             VLMFW_CUDA_OK(cudaMemcpyAsync(*s.master, src, static_cast<size_t>(numel) * 4, cudaMemcpyDeviceToDevice, st));
         } else {
-            int rc = launch_pack_16(src, s.rows, s.cols, *s.dst, s.ld, t->f16, st);
+            const float scale = t->f16 ? fp16_weight_scale(amax) : 1.f;
+            if (s.scale != nullptr) *s.scale = scale;
+            rc = launch_pack_16(src, s.rows, s.cols, *s.dst, s.ld, t->f16, st, 1.f / scale);
             if (rc != VLMFW_OK) return rc;
         }
     } else {
@@ -329,6 +362,41 @@ extern "C" const void* vlmfw_tower_hidden16_ptr(const vlmfw_tower* t, void* work
     return static_cast<const uint8_t*>(workspace) + t->off_xn(batch);
 }
 
+extern "C" int vlmfw_tower_saturation(vlmfw_tower* t, int64_t* host_count, int32_t reset, void* stream) {
+    VLMFW_REQUIRE(t && host_count, "tower_saturation: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long v = 0;
+    VLMFW_CUDA_OK(cudaMemcpyAsync(&v, t->sat_dev, sizeof(v), cudaMemcpyDeviceToHost, st));
+    if (reset) VLMFW_CUDA_OK(cudaMemsetAsync(t->sat_dev, 0, sizeof(v), st));
+    VLMFW_CUDA_OK(cudaStreamSynchronize(st));
+    *host_count = static_cast<int64_t>(v);
+    return VLMFW_OK;
+}
+
+extern "C" int vlmfw_tower_weight_scale(const vlmfw_tower* t, const char* name, float* host_scale) {
+    VLMFW_REQUIRE(t && name && host_scale, "tower_weight_scale: null argument");
+    auto it = t->slots.find(name);
+    if (it == t->slots.end() || !it->second.matrix || it->second.scale == nullptr) {
+        set_error("tower_weight_scale: '%s' is not a weight matrix of this tower", name);
+        return VLMFW_E_NOTFOUND;
+    }
+    if (it->second.master != nullptr && !t->derived_ok) {
+        set_error("tower_weight_scale: '%s' is LayerNorm-folded; call vlmfw_tower_prepare first", name);
+        return VLMFW_E_STATE;
+    }
+    *host_scale = *it->second.scale;
+    return VLMFW_OK;
+}
+
+static int build_derived(vlmfw_tower* t, cudaStream_t st);
+extern "C" int vlmfw_tower_prepare(vlmfw_tower* t, void* stream) {
+    int rc = vlmfw_tower_ready(t);
+    if (rc != VLMFW_OK) return rc;
+    rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    return build_derived(t, static_cast<cudaStream_t>(stream));
+}
+
 static int build_derived(vlmfw_tower* t, cudaStream_t st) {
     if (t->derived_ok) return VLMFW_OK;
     if (!t->posb) VLMFW_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&t->posb), static_cast<size_t>(t->P) * t->D * 4));
@@ -339,13 +407,34 @@ static int build_derived(vlmfw_tower* t, cudaStream_t st) {
         rc = launch_add_rows(t->pos, t->cls, t->cls_pos0, 1, t->D, 0, st);
         if (rc != VLMFW_OK) return rc;
     }
-    // fold ln1 into the QKV projection and ln2 into fc1 (layernorm.cu: ln_fold_weight_kernel)
+    // fold ln1 into the QKV projection and ln2 into fc1 (layernorm.cu: ln_fold_weight_kernel). fp16 towers: the folded
+    // values are what gets rounded, so their max decides the operand scale — one extra pass only when it is needed.
+    auto fold = [&](const float* w32, int n, const float* g, const float* b, const float* bias, void* w16, float* c2,
+                    float* scale) -> int {
+        *scale = 1.f;
+        if (!t->f16) return launch_ln_fold_weight(w32, n, t->D, g, b, bias, w16, t->D, false, c2, st);
+        VLMFW_CUDA_OK(cudaMemsetAsync(t->amax_dev, 0, sizeof(unsigned int), st));
+        int r = launch_ln_fold_weight(w32, n, t->D, g, b, bias, w16, t->D, true, c2, st, 1.f, t->amax_dev);
+        if (r != VLMFW_OK) return r;
+        unsigned int bits = 0;
+        VLMFW_CUDA_OK(cudaMemcpyAsync(&bits, t->amax_dev, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        VLMFW_CUDA_OK(cudaStreamSynchronize(st));
+        float amax;
+        memcpy(&amax, &bits, sizeof(amax));
+        if (!(amax < 3.0e38f)) {
+            set_error("tower weights: a LayerNorm-folded matrix holds a non-finite value");
+            return VLMFW_E_RANGE;
+        }
+        *scale = fp16_weight_scale(amax);
+        if (*scale != 1.f) r = launch_ln_fold_weight(w32, n, t->D, g, b, bias, w16, t->D, true, c2, st, 1.f / *scale);
+        return r;
+    };
     for (auto& w : t->layers) {
         if (!w.c2qkv) VLMFW_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&w.c2qkv), static_cast<size_t>(3 * t->D) * 4));
         if (!w.c2fc1) VLMFW_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&w.c2fc1), static_cast<size_t>(t->I) * 4));
-        rc = launch_ln_fold_weight(w.wqkv32, 3 * t->D, t->D, w.ln1w, w.ln1b, w.bqkv, w.wqkv, t->D, t->f16, w.c2qkv, st);
+        rc = fold(w.wqkv32, 3 * t->D, w.ln1w, w.ln1b, w.bqkv, w.wqkv, w.c2qkv, &w.s_qkv);
         if (rc != VLMFW_OK) return rc;
-        rc = launch_ln_fold_weight(w.w132, t->I, t->D, w.ln2w, w.ln2b, w.b1, w.w1, t->D, t->f16, w.c2fc1, st);
+        rc = fold(w.w132, t->I, w.ln2w, w.ln2b, w.b1, w.w1, w.c2fc1, &w.s_fc1);
         if (rc != VLMFW_OK) return rc;
     }
     t->derived_ok = true;
@@ -391,6 +480,8 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.lda = t->kpad;
         g.f16 = t->f16;
         g.w = t->patch_w;
+        g.acc_scale = t->s_patch;
+        g.sat_count = t->f16 ? t->sat_dev : nullptr;
         g.ldw = t->kpad;
         g.m = batch * P;
         g.n = D;
@@ -427,7 +518,7 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
     // ---- encoder layers (pre-LN transformer blocks). No LayerNorm kernel runs in here: ln1 / ln2 are folded into the
     // QKV / fc1 GEMMs; the out-proj / fc2 epilogues leave the 16-bit copy of h (xn) and its row statistics behind.
     if (!head_done) {
-        rc = launch_row_stats_cast(h, M, D, xn, t->f16, stats, np, st);
+        rc = launch_row_stats_cast(h, M, D, xn, t->f16, stats, np, st, t->f16 ? t->sat_dev : nullptr);
         if (rc != VLMFW_OK) return rc;
     }
     for (int li = 0; li < t->L; ++li) {
@@ -436,6 +527,8 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.a = xn;
         g.lda = D;
         g.w = w.wqkv;
+        g.acc_scale = w.s_qkv;
+        g.sat_count = t->f16 ? t->sat_dev : nullptr;
         g.f16 = t->f16;
         g.ldw = D;
         g.m = M;
@@ -458,6 +551,8 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.a = ctx;
         g.lda = D;
         g.w = w.wo;
+        g.acc_scale = w.s_o;
+        g.sat_count = t->f16 ? t->sat_dev : nullptr;
         g.f16 = t->f16;
         g.ldw = D;
         g.m = M;
@@ -484,6 +579,8 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.a = xn;
         g.lda = D;
         g.w = w.w1;
+        g.acc_scale = w.s_fc1;
+        g.sat_count = t->f16 ? t->sat_dev : nullptr;
         g.f16 = t->f16;
         g.ldw = D;
         g.m = M;
@@ -504,6 +601,8 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.a = mid;
         g.lda = t->Ild();
         g.w = w.w2;
+        g.acc_scale = w.s_fc2;
+        g.sat_count = t->f16 ? t->sat_dev : nullptr;
         g.f16 = t->f16;
         g.ldw = t->Ild();
         g.m = M;
@@ -637,6 +736,8 @@ extern "C" int vlmfw_gemm_tn_ex(const vlmfw_gemm_desc* d, void* stream) {
     g.h16_out = d->h16_out;
     g.ld_h16 = d->ld_h16;
     g.stats_out = d->stats_out;
+    g.acc_scale = d->acc_scale > 0.f ? d->acc_scale : 1.f;
+    g.sat_count = static_cast<unsigned long long*>(d->sat_count);
     return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 

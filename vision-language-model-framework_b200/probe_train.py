@@ -47,10 +47,13 @@ class ProbeTrainStep:
     def __init__(self, dim: int, classes: int, device="cuda", lr: float = 1e-4, weight_decay: float = 1e-4,
                  betas=(0.9, 0.999), eps: float = 1e-8, dropout_p: float = 0.3,
                  class_weight: Optional[torch.Tensor] = None, bn_eps: float = 1e-5, bn_momentum: float = 0.1,
-                 seed: int = 0, group=None):
+                 seed: int = 0, group=None, comm: str = "auto"):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("ProbeTrainStep runs on CUDA only: vlmfw_b200 has no CPU fallback")
+        if comm not in ("auto", "nccl"):
+            raise ValueError("comm must be 'auto' or 'nccl'")
+        self.comm = "nccl"
         self.dim, self.classes = dim, classes
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.dropout_p, self.bn_eps, self.bn_momentum = dropout_p, bn_eps, bn_momentum
@@ -76,6 +79,43 @@ class ProbeTrainStep:
         self.weight.copy_((torch.rand(classes, dim, generator=g) * 2 - 1) * bound)
         self.bias.copy_((torch.rand(classes, generator=g) * 2 - 1) * bound)
         self.gamma.fill_(1.0)
+
+    # kernels of this library per graph-form step: bn_stats, dropout_mask, probe_train_fwd, probe_train_bwd, adamw,
+    # bn_running, counter_add (csrc/probe.cu); NCCL's all-reduce kernels are not counted
+    kernels_per_step = 7
+
+    def exchange_description(self) -> str:
+        return ("2 dependent NCCL all-reduces per step: BatchNorm batch sums [2D] fp64, then the flat gradient bucket "
+                "[C*D + C + 2D + 2] fp32")
+
+    def exchange_report(self, steps: int = 200) -> dict:
+        """Latency of the step's exchange measured in isolation: ``steps`` DEPENDENT all-reduces of each of the two
+        buffers, captured in one CUDA graph like the train step, timed with CUDA events (max over ranks)."""
+        import torch.distributed as dist
+
+        dev = self.device
+        out = {}
+        for name, buf in (("bn_sums_f64", torch.zeros_like(self.stats)), ("grad_bucket_f32", torch.zeros_like(self.bucket))):
+            allreduce_sum_(buf, self.group)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(steps):
+                    allreduce_sum_(buf, self.group)
+            g.replay()
+            torch.cuda.synchronize(dev)
+            dist.barrier(self.group)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=self.group)
+            out[name] = {"bytes": buf.numel() * buf.element_size(), "us_per_allreduce": round(float(ms.item()) * 1e3 / steps, 2)}
+            del g
+        out["method"] = f"{steps} dependent ncclAllReduce calls replayed from one CUDA graph, CUDA events, max over ranks"
+        return out
 
     # views into the flat vector
     @property

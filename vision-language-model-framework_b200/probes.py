@@ -67,7 +67,10 @@ def fused_heads_forward(feats: torch.Tensor, heads: Sequence[nn.Sequential],
             _lib.check(_lib.load().vlmfw_probe_forward(
                 feats.data_ptr(), b, dim, descs, len(heads), logits.data_ptr(), off,
                 None if amax is None else amax.data_ptr(), torch.cuda.current_stream(feats.device).cuda_stream))
-    return list(logits.split(widths, dim=1)), amax
+    parts = list(logits.split(widths, dim=1))
+    if len(parts) > 1:  # the reference's heads return contiguous [B, C_t] tensors
+        parts = [p.contiguous() for p in parts]
+    return parts, amax
 
 
 class BaseProbe(nn.Module):
@@ -110,12 +113,84 @@ class BaseProbe(nn.Module):
             p.requires_grad = not freeze
         self._fully_frozen = self._compute_fully_frozen()
 
+    @torch.no_grad()
+    def predict_stream(self, batches):
+        """``predict`` over an iterable of batches as a generator, software-pipelined so the GPU never waits for the host:
+        the host->device copy of batch i+1 runs on the backbone's copy stream while batch i computes
+        (``B200VisionBackbone.stage_async``), and the labels of batch i are read back (pinned buffer, async copy) after
+        batch i+1 has been enqueued. Yields, in order, exactly what ``predict(batch)`` returns, as CPU tensors (or a dict
+        of CPU tensors for a multitask probe). The reference's tester loop (probing/test/base_tester.py:47-61) is the
+        serial form of this: one blocking ``.cpu()`` per batch (singletask_tester.py:98)."""
+        stage = getattr(self.backbone, "stage_async", None)
+        it = iter(batches)
+
+        def staged():
+            try:
+                nxt = next(it)
+            except StopIteration:
+                return
+            cur = stage(nxt) if stage is not None else nxt
+            while True:
+                try:
+                    nxt = next(it)
+                except StopIteration:
+                    yield cur
+                    return
+                ahead = stage(nxt) if stage is not None else nxt  # issued before `cur` is consumed: overlaps its forward
+                yield cur
+                cur = ahead
+
+        ring, pending, k = [None, None], None, 0
+
+        def finish(p):
+            host, ev, names = p
+            ev.synchronize()
+            out = host.clone()
+            return out if names is None else {t: out[:, i] for i, t in enumerate(names)}
+
+        for batch in staged():
+            pred = self.predict(batch)
+            names = None
+            if isinstance(pred, dict):
+                names = list(pred.keys())
+                pred = torch.stack([pred[t] for t in names], dim=1)
+            slot = k & 1
+            k += 1
+            if ring[slot] is None or ring[slot].shape != pred.shape or ring[slot].dtype != pred.dtype:
+                ring[slot] = torch.empty(pred.shape, dtype=pred.dtype).pin_memory() if pred.is_cuda else None
+            if pred.is_cuda:
+                ring[slot].copy_(pred, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(pred.device))
+                cur = (ring[slot], ev, names)
+            else:
+                cur = None
+            if pending is not None:
+                yield finish(pending)
+            if cur is None:  # CPU predictions (no device work to pipeline)
+                yield pred if names is None else {t: pred[:, i] for i, t in enumerate(names)}
+                pending = None
+            else:
+                pending = cur
+        if pending is not None:
+            yield finish(pending)
+
     # fused eval path is taken when nothing needs autograd and everything is fp32 on the GPU
     def _use_fused(self, feats: torch.Tensor, heads: Sequence[nn.Module]) -> bool:
         if not feats.is_cuda or torch.is_grad_enabled() and any(p.requires_grad for h in heads for p in h.parameters()):
             return False
         if any(h.training for h in heads):
             return False
+        # limits of vlmfw_probe_forward (csrc/probe.cu): <= 16 heads, <= 32 classes per head, and the staged row
+        # (dim + hidden + 32 floats) inside 48 KB of shared memory; anything else runs the nn.Sequential path
+        if len(heads) > 16:
+            return False
+        for h in heads:
+            deeper = len(h) == 6
+            classes = (h[5] if deeper else h[2]).out_features
+            hidden = h[2].out_features if deeper else 0
+            if classes > 32 or (feats.shape[-1] + hidden + 32) * 4 > 48 * 1024:
+                return False
         return all(p.dtype == torch.float32 and p.is_cuda for h in heads for p in h.parameters())
 
 

@@ -54,6 +54,20 @@ class VisionBackbone(nn.Module, ABC):
 ImagesLike = Union["PIL.Image.Image", Sequence, torch.Tensor]  # noqa: F821
 
 
+class StagedBatch:
+    """A batch whose host->device copy was issued on the backbone's copy stream (``B200VisionBackbone.stage_async``):
+    ``tensor`` is the device buffer, ``ready`` the event the consuming stream waits on. Passing it where images are
+    expected (``backbone(staged)``, ``probe.predict(staged)``) makes the forward wait for the copy instead of issuing it."""
+
+    __slots__ = ("tensor", "ready", "slot")
+
+    def __init__(self, tensor: torch.Tensor, ready: "torch.cuda.Event", slot: int):
+        self.tensor, self.ready, self.slot = tensor, ready, slot
+
+    def __len__(self) -> int:
+        return int(self.tensor.shape[0])
+
+
 class B200VisionBackbone(VisionBackbone):
     """Common machinery of the three B200 adapters: spec inference, weight packing, input staging."""
 
@@ -78,6 +92,11 @@ class B200VisionBackbone(VisionBackbone):
         self._ingest: Dict[str, ImageIngest] = {}
         self.gpu_ingest = os.environ.get("VLMFW_INGEST", "gpu") != "hf"
         self._weights_version = 0
+        # double-buffered input staging (stage_async): copy stream, two device buffers, "buffer consumed" events
+        self._copy_stream: Dict[str, "torch.cuda.Stream"] = {}
+        self._stage_bufs: Dict[tuple, torch.Tensor] = {}
+        self._stage_free: Dict[tuple, "torch.cuda.Event"] = {}
+        self._stage_next = 0
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed_weights())
 
     # -- weights -------------------------------------------------------------------------------------------------
@@ -120,6 +139,9 @@ class B200VisionBackbone(VisionBackbone):
         call for such images instead (CPU bicubic resize, fp32 NCHW ingest).
         """
         s = self.spec.image_size
+        if isinstance(images, StagedBatch):
+            torch.cuda.current_stream(dev).wait_event(images.ready)
+            return images.tensor
         if isinstance(images, torch.Tensor):
             t = images
             if t.dtype == torch.uint8:
@@ -158,10 +180,53 @@ class B200VisionBackbone(VisionBackbone):
         pv = inputs["pixel_values"].to(torch.float32).contiguous()
         return pv.pin_memory().to(dev, non_blocking=True)
 
+    def stage_async(self, images: ImagesLike) -> StagedBatch:
+        """Start the host->device copy of a batch on the backbone's copy stream and return at once.
+
+        The synchronous path (``_stage_pixels``) copies on the compute stream, so copy and tower forward serialise (2 % of
+        a SigLIP batch-256 step). Here the copy of batch i+1 runs on its own stream into the other one of two device buffers
+        while batch i computes; a buffer is rewritten only after the forward that read it has been enqueued AND finished
+        (event recorded by ``_features``). Host side: a pinned uint8 / fp32 tensor is copied as is; anything else goes
+        through ``_stage_pixels`` on the copy stream."""
+        dev = self._tower_device()
+        if dev.type != "cuda":
+            raise RuntimeError(f"{type(self).__name__}.stage_async: the tower lives on '{dev}'; there is no CPU fallback")
+        key = str(dev)
+        cs = self._copy_stream.get(key)
+        if cs is None:
+            cs = self._copy_stream[key] = torch.cuda.Stream(device=dev)
+        slot = self._stage_next & 1
+        self._stage_next += 1
+        free = self._stage_free.get((key, slot))
+        if free is not None:
+            cs.wait_event(free)
+        with torch.cuda.stream(cs):
+            if isinstance(images, torch.Tensor) and images.device.type == "cpu" and images.is_pinned() \
+                    and images.dtype in (torch.uint8, torch.float32) and images.dim() == 4:
+                bkey = (key, slot, tuple(images.shape), images.dtype)
+                buf = self._stage_bufs.get(bkey)
+                if buf is None:
+                    for k in [k for k in self._stage_bufs if k[:2] == (key, slot)]:
+                        del self._stage_bufs[k]
+                    buf = self._stage_bufs[bkey] = torch.empty(images.shape, dtype=images.dtype, device=dev)
+                buf.copy_(images, non_blocking=True)
+                t = buf
+            else:
+                t = self._stage_pixels(images, dev)
+                t.record_stream(torch.cuda.current_stream(dev))
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        return StagedBatch(t, ready, slot)
+
     def _features(self, images: ImagesLike, pool: int) -> torch.Tensor:
         eng = self._engine(pool)
         with torch.no_grad():  # the reference wraps the tower call in no_grad unconditionally (paligemma.py:110)
-            return eng.forward(self._stage_pixels(images, eng.device))
+            out = eng.forward(self._stage_pixels(images, eng.device))
+        if isinstance(images, StagedBatch):  # the staging buffer may be rewritten once this forward has run
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(eng.device))
+            self._stage_free[(str(eng.device), images.slot)] = ev
+        return out
 
     # -- reference utilities kept as thin name-matching helpers ----------------------------------------------------
     _ATTN_KEYS: Sequence[str] = (".self_attn.q_proj", ".self_attn.k_proj", ".self_attn.v_proj", ".self_attn.out_proj")
