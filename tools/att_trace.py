@@ -15,14 +15,17 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vlmfw_b200 import ops, _lib
 lib = _lib.load()
-lib.vlmfw_debug_att_trace.argtypes = [C.c_void_p]
-bsz, s, hd, dh = (256, 256, 16, 72) if len(sys.argv) < 2 or sys.argv[1] == "siglip" else (113, 577, 16, 64)
+# VLMFW_ATTN=tc traces the round-1 kernel (attention_tc.cu), otherwise the wide-block kernel (attention_wb.cu)
+fetch = lib.vlmfw_debug_att_trace if os.environ.get("VLMFW_ATTN", "wb").startswith("t") else lib.vlmfw_debug_wb_trace
+fetch.argtypes = [C.c_void_p]
+which = sys.argv[1] if len(sys.argv) > 1 else "siglip"
+bsz, s, hd, dh = {"siglip": (256, 256, 16, 72), "clip": (128, 577, 16, 64), "eva": (128, 257, 16, 88)}[which]
 qkv = (torch.randn(bsz * s, 3 * hd * dh, device="cuda") * 0.5).to(torch.float16)
 for _ in range(3):
     ops.attention(qkv, bsz, s, hd, dh)
 torch.cuda.synchronize()
 buf = np.zeros((4, 8192), np.int64)
-assert lib.vlmfw_debug_att_trace(buf.ctypes.data) == 0
+assert fetch(buf.ctypes.data) == 0
 names = {0: "loader", 1: "s-issuer", 2: "softmax", 3: "pv-issuer"}
 for role in range(4):
     ev = buf[role]

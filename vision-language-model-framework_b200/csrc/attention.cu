@@ -258,6 +258,16 @@ int launch_attention(const void* qkv, bool f16, int batch, int tokens, int heads
     // that one row costs more than the tcgen05 kernel's third, mostly idle, work item (0.445 vs 0.412 ms at B = 255), so
     // the split stays off and the tcgen05 kernel skips the arithmetic of softmax warps whose rows lie past the sequence.
     const int q_tail = tokens;
+    // Second-generation tcgen05 kernel (attention_wb.cu: 128-key blocks, P kept in tensor memory) first; VLMFW_ATTN=tc
+    // pins the round-1 kernel (attention_tc.cu) for A/B timing, and it stays the fallback for shapes wb does not cover.
+    static const bool wb_on = []() {
+        const char* e = getenv("VLMFW_ATTN");
+        return !(e != nullptr && e[0] == 't');
+    }();
+    if (!legacy && wb_on) {
+        rc = launch_attention_wb(qkv, f16, batch, tokens, heads, head_dim, out, stream);
+        if (rc <= 0) return rc;
+    }
     if (!legacy) {
         rc = launch_attention_tc(qkv, f16, batch, tokens, heads, head_dim, out, q_tail, stream);
         if (rc < 0) return rc;

@@ -9,7 +9,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompil
        --expt-relaxed-constexpr -Xptxas -v ${VLMFW_EXTRA_FLAGS:-})
 mkdir -p "${BUILD}"
 pids=()
-for f in gemm_tcgen05 layernorm embed attention attention_tc probe probe_deep preprocess sink tower; do
+for f in gemm_tcgen05 layernorm embed attention attention_tc attention_wb probe probe_deep preprocess sink tower; do
   ( "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${BUILD}/${f}.o" > "${BUILD}/${f}.log" 2>&1 ) &
   pids+=($!)
 done

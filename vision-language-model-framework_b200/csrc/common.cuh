@@ -127,6 +127,9 @@ int launch_attention(const void* qkv, bool f16, int batch, int tokens, int heads
 // Only query rows [0, q_rows) are computed (q_rows a multiple of 128, or == tokens); all `tokens` keys are attended.
 int launch_attention_tc(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out,
                         int q_rows, cudaStream_t stream);
+// second-generation tcgen05 attention (attention_wb.cu): 0 = launched, 1 = shape not covered, <0 = error
+int launch_attention_wb(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out,
+                        cudaStream_t stream);
 int launch_im2col(const void* pixels, int pix_fmt, int batch, int image_size, int patch, const float* mean3,
                   const float* std3, void* out, int kpad, bool out_f16, cudaStream_t stream);
 int launch_fill_cls(const float* cls_pos0, float* h, int batch, int tokens, int dim, cudaStream_t stream);
