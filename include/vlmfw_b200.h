@@ -147,6 +147,15 @@ int vlmfw_tower_ready(vlmfw_tower* t);
 int vlmfw_tower_prepare(vlmfw_tower* t, void* stream);
 /* Power-of-two scale the 16-bit operand of weight matrix `name` is stored divided by (1 unless max |W| > 32768). */
 int vlmfw_tower_weight_scale(const vlmfw_tower* t, const char* name, float* host_scale);
+/* Class-token-pooled towers (VLMFW_POOL_CLS: llava.py:114-115; VLMFW_POOL_LN_CLS_LN: blip2.py:94-95) run their LAST encoder
+ * layer for the class-token rows only by default: K / V of every row, then Q, one-query attention, out-proj and the MLP as
+ * M = B GEMMs over rows b*S. The pooled features are those of the full layer (same kernels' arithmetic on the rows that
+ * matter; attention probabilities stay fp32); rows 1..S-1 of the final residual stream keep the previous layer's values.
+ * enable = 0 computes the whole last layer (callers that read vlmfw_tower_hidden_ptr); VLMFW_CLS_TAIL=0 in the environment
+ * sets that default at creation. Enabling it on a tower whose pooling reads other rows fails with VLMFW_E_INVALID. */
+int vlmfw_tower_set_cls_tail(vlmfw_tower* t, int32_t enable);
+int32_t vlmfw_tower_cls_tail(const vlmfw_tower* t);
+
 /* fp16 towers: number of 16-bit activation stores (one thread's 32-column chunk of one row of the QKV / fc1 outputs or of
  * the residual stream) in which at least one value was clamped to +-65504 since creation / the last reset. 0 means no
  * forward clipped. Synchronises `stream`. bf16 towers always report 0 (fp32 exponent range). */
@@ -257,6 +266,37 @@ int vlmfw_dropout_keep_mask_dev(uint8_t* keep, int32_t rows, int32_t cols, int64
                                 const int64_t* steps_done, uint64_t step_stride, float dropout_p, void* stream);
 int vlmfw_counter_add(int64_t* counter, int64_t inc, void* stream);
 
+/* Data-parallel exchange of the train step over NVLink peer memory, fused into the step's own kernels (BASELINE configs[4]:
+ * "only the tiny probe-weight gradients are allreduced"; the reference itself has no multi-GPU training —
+ * probing/train/base_trainer.py:30). One process per GPU of ONE node. Each rank creates a communicator (one exchange
+ * buffer: flags + per-rank slots for the BatchNorm sums [2D] fp64 and the gradient bucket [C*D + C + 2D + 2] fp32), the host
+ * exchanges the handles (vlmfw_comm_handle -> all-gather -> vlmfw_comm_connect maps every peer's buffer with cudaIpc), and
+ * vlmfw_probe_linear_step_dp then runs whole optimisation steps: the producing kernels store their rank's sums straight into
+ * every peer's slots and raise per-CTA flags, the consuming kernels wait on their local flags and add the slots in rank
+ * order (bit-identical parameters on all ranks). No collective kernel is launched. world == 1 needs no connect. */
+typedef struct vlmfw_comm vlmfw_comm;
+int vlmfw_comm_create(int32_t rank, int32_t world, int64_t stats_doubles, int64_t bucket_floats, vlmfw_comm** out);
+int32_t vlmfw_comm_handle_bytes(void);
+int vlmfw_comm_handle(vlmfw_comm* c, void* handle_out);
+int vlmfw_comm_connect(vlmfw_comm* c, const void* handles);
+void vlmfw_comm_destroy(vlmfw_comm* c);
+/* *host_flag = 1 when a wait gave up because a peer stopped reporting (results since then are invalid) */
+int vlmfw_comm_error(vlmfw_comm* c, int32_t* host_flag);
+/* one optimisation step of the linear head (probing/train/singletask_trainer.py:183-191 + base_trainer.py:166-181) as seven
+ * launches: bn_stats, dropout mask (+ combine of the ranks' BatchNorm sums), forward, backward, AdamW (+ combine of the ranks'
+ * gradient buckets), BatchNorm running statistics, step counter. params / moments are the flat vector
+ * [W (C*D) | b (C) | gamma (D) | beta (D)]; bucket [n_params + 2] receives the all-reduced [loss_sum, weight_sum] in its
+ * last two entries; keep uint8 [batch, dim] (16-byte aligned; unused when dropout_p == 0); scratch fp32 [batch * (classes + 2)];
+ * *steps_done = optimisation steps completed so far (advanced by this call's last kernel). */
+typedef struct vlmfw_probe_step {
+    const float* x; const int64_t* targets; int32_t batch, dim, classes, n_global; int64_t row0;
+    double* stats; float* params; float* exp_avg; float* exp_avg_sq; float* bucket; float* logits; float* scratch;
+    uint8_t* keep; const float* class_weight; float* running_mean; float* running_var; int64_t* steps_done;
+    uint64_t mask_key, mask_step_stride;
+    float dropout_p, bn_eps, bn_momentum, lr, beta1, beta2, eps, weight_decay;
+} vlmfw_probe_step;
+int vlmfw_probe_linear_step_dp(const vlmfw_probe_step* a, vlmfw_comm* c, void* stream);
+
 /* ------------------------------------------------------------------ tester sink
  * Per-task confusion counts of a batch of predictions, accumulated on the device: counts [tasks, classes, classes] int32
  * (row = ground truth, column = prediction — sklearn.metrics.confusion_matrix as the reference's Evaluator calls it,
@@ -315,6 +355,10 @@ int vlmfw_layernorm(const float* x, int32_t rows, int32_t dim, const float* gamm
  * inside each third; out same dtype [B*S, D]. head_dim in {64, 72, 88} (or any multiple of 8 <= 96). */
 int vlmfw_attention(const void* qkv, int32_t dtype, int32_t batch, int32_t tokens, int32_t heads, int32_t head_dim,
                     void* out, void* stream);
+/* attention of query row 0 of every image over all `tokens` keys (the last layer of a class-token-pooled tower):
+ * out 16-bit [batch, ld_out] compact, head-major columns like vlmfw_attention */
+int vlmfw_attention_cls(const void* qkv, int32_t dtype, int32_t batch, int32_t tokens, int32_t heads, int32_t head_dim,
+                        void* out, int32_t ld_out, void* stream);
 /* patch gather: pixels -> A [B*P, kpad] (out_dtype VLMFW_DT_*) with k = c*p*p + ky*p + kx (conv weight flattening),
  * zero padded */
 int vlmfw_im2col(const void* pixels, int32_t pix_fmt, int32_t batch, int32_t image_size, int32_t patch_size,

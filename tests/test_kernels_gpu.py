@@ -296,6 +296,25 @@ def _attn_ref(qkv, batch, tokens, heads, dh):
     return (att @ v).transpose(1, 2).reshape(batch * tokens, d)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("batch,tokens,heads,dh", [(5, 257, 16, 88), (3, 577, 16, 64), (4, 17, 2, 72), (2, 1030, 3, 8),
+                                                   (2, 50, 4, 128)])
+def test_attention_cls(cuda_device, batch, tokens, heads, dh, dtype):
+    """One-query attention (the class-token row of the last layer, hf sdpa_attention.py:92 restricted to query 0): fp32
+    probabilities, so only the 16-bit output rounding separates it from the fp32 reference."""
+    d = heads * dh
+    qkv = _rand((batch * tokens, 3 * d), 33, 1.5).to(dtype)
+    out = ops.attention_cls(qkv, batch, tokens, heads, dh)
+    ref = _attn_ref(qkv, batch, tokens, heads, dh).view(batch, tokens, d)[:, 0]
+    tol = 8e-3 if dtype == torch.bfloat16 else 1e-3
+    assert out.dtype == dtype and tuple(out.shape) == (batch, d)
+    torch.testing.assert_close(out.float(), ref, rtol=tol, atol=tol)
+    # and it agrees with row 0 of the all-queries kernel wherever that kernel covers the shape
+    if dh <= 96:
+        full = ops.attention(qkv, batch, tokens, heads, dh).view(batch, tokens, d)[:, 0]
+        torch.testing.assert_close(out.float(), full.float(), rtol=4 * tol, atol=4 * tol)
+
+
 @pytest.mark.parametrize("batch,tokens,heads,dh", [(24, 256, 16, 72), (7, 577, 16, 64), (9, 257, 16, 88)])
 def test_attention_persistent_many_items(cuda_device, batch, tokens, heads, dh):
     """More work items than SMs: every CTA of the persistent tcgen05 kernel loops over several (image, head, query-pair)

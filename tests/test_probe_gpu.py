@@ -138,19 +138,21 @@ def test_device_keep_mask_is_shard_invariant_and_bernoulli(cuda_device):
     assert torch.equal(ts.dropout_keep_mask(n, 100, 356), full[100:356])
 
 
+@pytest.mark.parametrize("comm", ["auto", "p2p"])
 @pytest.mark.parametrize("p", [0.3, 0.0])
-def test_graph_step_equals_eager_step(cuda_device, p):
+def test_graph_step_equals_eager_step(cuda_device, p, comm):
     """The train step replayed from one CUDA graph (device-side step counter for AdamW's bias corrections and the dropout
     key) = the eager step: same masks bit for bit, same losses and parameters (bias corrections come from the device's
-    powf instead of the host's), also when eager and graph steps alternate."""
+    powf instead of the host's), also when eager and graph steps alternate. comm="p2p" runs the fused-exchange form
+    (vlmfw_probe_linear_step_dp) as a one-rank communicator: its own slots, flags and epoch counter, same arithmetic."""
     d, c, n, steps = 1152, 9, 256, 6
     g = torch.Generator().manual_seed(5)
     cw = torch.rand(c, generator=g) + 0.5
     xs = [(torch.randn(n, d, generator=g) * 1.3 + 0.2).cuda() for _ in range(steps)]
     ys = [torch.randint(-1, c, (n,), generator=g).cuda() for _ in range(steps)]
     eager = ProbeTrainStep(d, c, device=cuda_device, class_weight=cw, dropout_p=p, seed=3)
-    graph = ProbeTrainStep(d, c, device=cuda_device, class_weight=cw, dropout_p=p, seed=3)
-    mixed = ProbeTrainStep(d, c, device=cuda_device, class_weight=cw, dropout_p=p, seed=3)
+    graph = ProbeTrainStep(d, c, device=cuda_device, class_weight=cw, dropout_p=p, seed=3, comm=comm)
+    mixed = ProbeTrainStep(d, c, device=cuda_device, class_weight=cw, dropout_p=p, seed=3, comm=comm)
     graph.capture(n)
     with pytest.raises(ValueError):
         graph.step_graph(xs[0][:7], ys[0][:7])
@@ -176,3 +178,22 @@ def test_graph_step_equals_eager_step(cuda_device, p):
         torch.testing.assert_close(other.exp_avg_sq, eager.exp_avg_sq, rtol=1e-6, atol=1e-12)
         torch.testing.assert_close(other.running_var, eager.running_var, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(graph.last_logits, eager.last_logits, rtol=1e-5, atol=1e-6)
+    for other in (graph, mixed):
+        assert not other.comm_error()
+        other.release_graph()
+
+
+def test_all_ignored_batch_skips_the_update(cuda_device):
+    """Every target -1: the reference's loss is 0/0 (NaN into the head); this step reports loss 0.0 and leaves parameters
+    and moments untouched, eager and graph form alike (documented deviation, DESIGN.md numerics)."""
+    d, c, n = 64, 5, 16
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(0)).cuda()
+    y = torch.full((n,), -1, dtype=torch.int64).cuda()
+    for comm in ("auto", "p2p"):
+        ts = ProbeTrainStep(d, c, device=cuda_device, dropout_p=0.0, seed=3, comm=comm)
+        before = ts.params.clone()
+        assert ts.step(x, y) == 0.0
+        ts.capture(n)
+        assert ts.step_graph(x, y) == 0.0
+        assert torch.equal(ts.params, before) and float(ts.exp_avg_sq.abs().max()) == 0.0
+        ts.release_graph()

@@ -19,9 +19,20 @@ def _run(spec, n_img, seed, smooth, fmt, compute_dtype="f16"):
     eng.load_hf_state_dict(sd)
     imgs = weights.seeded_images_u8(n_img, spec.image_size, seed, smooth=smooth)
     pv = O.preprocess_u8(imgs, spec.pix_mean, spec.pix_std)
-    got = eng.forward(imgs.cuda() if fmt == "u8" else pv.contiguous().cuda())
+    dev_in = imgs.cuda() if fmt == "u8" else pv.contiguous().cuda()
+    got = eng.forward(dev_in)
     torch.cuda.synchronize()
-    hid = eng.hidden_state(n_img).float().cpu()
+    if eng.cls_tail:
+        # class-token-pooled towers run their last layer for row 0 only: the features above come from that path; the
+        # full residual stream the callers compare needs the whole last layer — and must pool to the same features
+        eng.set_cls_tail(False)
+        full = eng.forward(dev_in)
+        torch.cuda.synchronize()
+        assert (full - got).abs().max() <= 2e-3 * max(1.0, full.abs().max().item()), (full - got).abs().max()
+        hid = eng.hidden_state(n_img).float().cpu()
+        eng.set_cls_tail(True)
+    else:
+        hid = eng.hidden_state(n_img).float().cpu()
     can = weights.hf_to_canonical(spec, sd)
     ref = O.tower_features(spec, can, pv)
     ref_hid = O.last_hidden(spec, {k: v.float() for k, v in can.items()}, pv)
@@ -99,6 +110,9 @@ def test_massive_activation_channels(cuda_device, monkeypatch, name, residual):
     eng.load_hf_state_dict(sd)
     imgs = weights.seeded_images_u8(4, spec.image_size, 9, smooth=True)
     got = eng.forward(imgs.cuda()).cpu()
+    if eng.cls_tail:
+        eng.set_cls_tail(False)
+        eng.forward(imgs.cuda())
     hid = eng.hidden_state(4).float().cpu()
     pv = O.preprocess_u8(imgs, spec.pix_mean, spec.pix_std)
     can = weights.hf_to_canonical(spec, sd)

@@ -65,6 +65,23 @@ def main():
     dp_losses = [dp.step(xs[s, tlo:thi].to(dev), ys[s, tlo:thi].to(dev), n_global=nb, global_offset=tlo) for s in range(steps)]
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
+    # the graph form of the same steps, once per exchange: fused NVLink peer-memory slots (p2p) and NCCL all-reduces
+    graph_runs = {}
+    for comm in ("p2p", "nccl"):
+        gs = ProbeTrainStep(d, c, device=dev, class_weight=cw, seed=3, comm=comm)
+        gs.capture(thi - tlo, n_global=nb, global_offset=tlo)
+        losses = [gs.step_graph(xs[s, tlo:thi].to(dev), ys[s, tlo:thi].to(dev)) for s in range(steps)]
+        bad = gs.comm_error()
+        # every rank must hold bit-identical parameters (the slots are added in rank order on every rank)
+        mine = gs.params.clone()
+        ref0 = mine.clone()
+        if env.is_distributed:
+            dist.broadcast(ref0, 0)
+        same = torch.tensor([1 if torch.equal(mine, ref0) else 0], device=dev)
+        if env.is_distributed:
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        graph_runs[comm] = (gs.params.clone(), losses, bool(same.item()), bad)
+        gs.release_graph()
     if env.rank == 0:
         single = ProbeTrainStep(d, c, device=dev, class_weight=cw, seed=3, group=False)
         single.group = None
@@ -83,6 +100,12 @@ def main():
                     "loss_max_abs_diff": lerr, "train_steps_per_s": round(steps / dt, 1),
                     "allreduce_bytes_per_step": 2 * d * 8 + (dp.n_params + 2) * 4})
         ok &= perr <= 1e-5 and lerr <= 1e-5
+        for comm, (gp, gl, same, bad) in graph_runs.items():
+            gerr = (gp - single.params).abs().max().item()
+            glerr = max(abs(a - b) for a, b in zip(gl, one_losses))
+            res[f"graph_{comm}"] = {"param_max_abs_diff_vs_single_process": gerr, "loss_max_abs_diff": glerr,
+                                    "params_bit_identical_across_ranks": same, "comm_error": bad}
+            ok &= gerr <= 1e-5 and glerr <= 1e-5 and same and not bad
         res["ok"] = bool(ok)
         print(json.dumps(res), flush=True)
     if env.is_distributed:

@@ -57,6 +57,18 @@ class GemmDesc(C.Structure):
     ]
 
 
+class ProbeStep(C.Structure):
+    """``vlmfw_probe_step``: every pointer / scalar of one fused data-parallel optimisation step."""
+    _fields_ = [
+        ("x", _vp), ("targets", _vp), ("batch", _i32), ("dim", _i32), ("classes", _i32), ("n_global", _i32), ("row0", _i64),
+        ("stats", _vp), ("params", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("bucket", _vp), ("logits", _vp),
+        ("scratch", _vp), ("keep", _vp), ("class_weight", _vp), ("running_mean", _vp), ("running_var", _vp),
+        ("steps_done", _vp), ("mask_key", C.c_uint64), ("mask_step_stride", C.c_uint64),
+        ("dropout_p", _f32), ("bn_eps", _f32), ("bn_momentum", _f32), ("lr", _f32), ("beta1", _f32), ("beta2", _f32),
+        ("eps", _f32), ("weight_decay", _f32),
+    ]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/vlmfw_b200.h
 SIGNATURES = {
     "vlmfw_abi_version": (C.c_int, []),
@@ -68,6 +80,8 @@ SIGNATURES = {
     "vlmfw_tower_ready": (C.c_int, [_vp]),
     "vlmfw_tower_prepare": (C.c_int, [_vp, _vp]),
     "vlmfw_tower_weight_scale": (C.c_int, [_vp, C.c_char_p, C.POINTER(_f32)]),
+    "vlmfw_tower_set_cls_tail": (C.c_int, [_vp, _i32]),
+    "vlmfw_tower_cls_tail": (_i32, [_vp]),
     "vlmfw_tower_saturation": (C.c_int, [_vp, C.POINTER(_i64), _i32, _vp]),
     "vlmfw_tower_workspace_bytes": (_sz, [_vp, _i32]),
     "vlmfw_tower_tokens": (_i32, [_vp]),
@@ -97,6 +111,13 @@ SIGNATURES = {
     "vlmfw_probe_adamw_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _vp]),
     "vlmfw_dropout_keep_mask_dev": (C.c_int, [_vp, _i32, _i32, _i64, C.c_uint64, _vp, C.c_uint64, _f32, _vp]),
     "vlmfw_counter_add": (C.c_int, [_vp, _i64, _vp]),
+    "vlmfw_comm_create": (C.c_int, [_i32, _i32, _i64, _i64, C.POINTER(_vp)]),
+    "vlmfw_comm_handle_bytes": (_i32, []),
+    "vlmfw_comm_handle": (C.c_int, [_vp, _vp]),
+    "vlmfw_comm_connect": (C.c_int, [_vp, _vp]),
+    "vlmfw_comm_destroy": (None, [_vp]),
+    "vlmfw_comm_error": (C.c_int, [_vp, C.POINTER(_i32)]),
+    "vlmfw_probe_linear_step_dp": (C.c_int, [C.POINTER(ProbeStep), _vp, _vp]),
     "vlmfw_gemm_tn": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
                                 _i32, _i32, _i32, _i32, _i32, _vp]),
     "vlmfw_gemm_tn_ex": (C.c_int, [C.POINTER(GemmDesc), _vp]),
@@ -105,6 +126,7 @@ SIGNATURES = {
     "vlmfw_ln_fold_weight": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "vlmfw_layernorm": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _f32, _vp, _i32, _vp]),
     "vlmfw_attention": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "vlmfw_attention_cls": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "vlmfw_im2col": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(_f32), C.POINTER(_f32), _vp, _i32, _i32, _vp]),
     "vlmfw_pool": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp]),
     "vlmfw_pack_16": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i32, _vp]),

@@ -237,6 +237,146 @@ int launch_att(const void* qkv, int batch, int tokens, int heads, int dh, void* 
     return VLMFW_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------- class-token query only
+// Last layer of a tower whose adapter keeps only the class token (blip2.py:94-95 pooler_output, llava.py:114-115 "cls"):
+// every other query row of that layer is dead work. One CTA = one (head, image): q = row 0, all `tokens` keys. A half-warp
+// owns a key (lane = 16-byte chunk of the head slice: 11 of 16 lanes busy at dh = 88, loads coalesced per key); scores, the
+// softmax and P.V stay fp32 (P is never rounded to 16 bits here). Fixed reduction order, deterministic. HBM-bound: the K
+// and V slices are read once (2 * tokens * dh * 2 bytes per CTA).
+constexpr int CLS_THREADS = 256;
+constexpr int CLS_HW = CLS_THREADS / 16;  // half-warps per CTA
+
+template <bool F16>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if constexpr (F16) {
+            const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            f[2 * i] = t.x;
+            f[2 * i + 1] = t.y;
+        } else {
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(CLS_THREADS) attention_cls_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out,
+                                                                    int tokens, int heads, int dh, int ld_out,
+                                                                    float scale_log2) {
+    extern __shared__ __align__(16) float cls_smem[];
+    const int dmodel = heads * dh;
+    const int chunks = dh >> 3;
+    float* sq = cls_smem;                 // [128] q * scale * log2(e)
+    float* sred = sq + 128;               // [16]
+    float* sacc = sred + 16;              // [CLS_HW][128] partial outputs
+    float* sp = sacc + CLS_HW * 128;      // [tokens] scores -> probabilities
+    const int head = blockIdx.x, img = blockIdx.y;
+    const size_t row_stride = static_cast<size_t>(3) * dmodel;
+    const uint16_t* base = qkv + static_cast<size_t>(img) * tokens * row_stride + static_cast<size_t>(head) * dh;
+    const int lane16 = threadIdx.x & 15, hw = threadIdx.x >> 4;
+    if (threadIdx.x < chunks) {
+        float f[8];
+        unpack8<F16>(*reinterpret_cast<const uint4*>(base + threadIdx.x * 8), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sq[threadIdx.x * 8 + i] = f[i] * scale_log2;
+    }
+    __syncthreads();
+    float q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = lane16 < chunks ? sq[lane16 * 8 + i] : 0.f;
+    const uint16_t* kb = base + dmodel + lane16 * 8;
+    const uint16_t* vb = base + 2 * dmodel + lane16 * 8;
+    // ---- scores (log2 domain)
+    for (int j0 = hw; j0 < tokens; j0 += 4 * CLS_HW) {
+        uint4 u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int j = j0 + i * CLS_HW;
+            u[i] = (j < tokens && lane16 < chunks) ? *reinterpret_cast<const uint4*>(kb + static_cast<size_t>(j) * row_stride)
+                                                   : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float f[8], d = 0.f;
+            unpack8<F16>(u[i], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d = fmaf(q[e], f[e], d);
+            d += __shfl_xor_sync(0xffffffffu, d, 8);
+            d += __shfl_xor_sync(0xffffffffu, d, 4);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            const int j = j0 + i * CLS_HW;
+            if (lane16 == 0 && j < tokens) sp[j] = d;
+        }
+    }
+    __syncthreads();
+    // ---- softmax: max and sum over the block (warp shuffles, then the 8 warp results in order)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float mx = -INFINITY;
+    for (int j = threadIdx.x; j < tokens; j += CLS_THREADS) mx = fmaxf(mx, sp[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) sred[warp] = mx;
+    __syncthreads();
+    mx = sred[0];
+#pragma unroll
+    for (int w = 1; w < CLS_THREADS / 32; ++w) mx = fmaxf(mx, sred[w]);
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < tokens; j += CLS_THREADS) {
+        const float e = exp2f(sp[j] - mx);
+        sp[j] = e;
+        sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();  // every thread has read sred (max) before it is reused
+    if (lane == 0) sred[8 + warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < CLS_THREADS / 32; ++w) sum += sred[8 + w];
+    // ---- P.V: half-warp hw takes keys hw, hw + 16, ...; lane = chunk of 8 output columns
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j0 = hw; j0 < tokens; j0 += 4 * CLS_HW) {
+        uint4 u[4];
+        float pj[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int j = j0 + i * CLS_HW;
+            const bool ok = j < tokens && lane16 < chunks;
+            u[i] = ok ? *reinterpret_cast<const uint4*>(vb + static_cast<size_t>(j) * row_stride) : make_uint4(0, 0, 0, 0);
+            pj[i] = j < tokens ? sp[j] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float f[8];
+            unpack8<F16>(u[i], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj[i], f[e], acc[e]);
+        }
+    }
+    if (lane16 < chunks) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sacc[hw * 128 + lane16 * 8 + e] = acc[e];
+    }
+    __syncthreads();
+    if (threadIdx.x < dh / 2) {
+        const int d = threadIdx.x * 2;
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int g = 0; g < CLS_HW; ++g) {
+            o0 += sacc[g * 128 + d];
+            o1 += sacc[g * 128 + d + 1];
+        }
+        const float inv = 1.f / sum;
+        *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(img) * ld_out + head * dh + d) = pack_16x2<F16>(o0 * inv, o1 * inv);
+    }
+}
+
 }  // namespace
 
 int launch_attention(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out,
@@ -282,6 +422,28 @@ int launch_attention(const void* qkv, bool f16, int batch, int tokens, int heads
     if (head_dim <= 64) return launch_att<64, false>(qkv, batch, tokens, heads, head_dim, out, stream, q_begin);
     if (head_dim <= 80) return launch_att<80, false>(qkv, batch, tokens, heads, head_dim, out, stream, q_begin);
     return launch_att<96, false>(qkv, batch, tokens, heads, head_dim, out, stream, q_begin);
+}
+
+int launch_attention_cls(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out, int ld_out,
+                         cudaStream_t stream) {
+    VLMFW_REQUIRE(qkv && out, "attention_cls: null pointer");
+    VLMFW_REQUIRE(batch > 0 && tokens > 0 && heads > 0, "attention_cls: bad shape");
+    VLMFW_REQUIRE(head_dim % 8 == 0 && head_dim >= 8 && head_dim <= 128, "attention_cls: head_dim %d unsupported", head_dim);
+    VLMFW_REQUIRE(batch <= 65535 && tokens <= 8192, "attention_cls: grid / sequence too large");
+    VLMFW_REQUIRE(ld_out >= heads * head_dim && ld_out % 2 == 0, "attention_cls: ld_out");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    const size_t smem = (128 + 16 + CLS_HW * 128 + static_cast<size_t>(tokens)) * sizeof(float);
+    const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
+    dim3 grid(heads, batch);
+    if (f16)
+        attention_cls_kernel<true><<<grid, CLS_THREADS, smem, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out),
+                                                                       tokens, heads, head_dim, ld_out, scale_log2);
+    else
+        attention_cls_kernel<false><<<grid, CLS_THREADS, smem, stream>>>(static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out),
+                                                                        tokens, heads, head_dim, ld_out, scale_log2);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
 }
 
 }  // namespace vlmfw

@@ -85,6 +85,7 @@ struct GemmArgs {
     const void* ln_stats = nullptr;
     int ln_np = 0, ln_dim = 0;
     float ln_eps = 0.f;
+    int ln_row_mul = 1;  // GEMM row m reads ln_stats row m * ln_row_mul (class-token rows of a [B*S] statistics table: S)
     // residual epilogue extras: 16-bit copy of the updated rows and their (sum, sum of squares) partials
     // ([M][gemm_stats_parts(n, block_n)] float2) for the LayerNorm folded into the NEXT GEMM
     void* h16_out = nullptr;
@@ -130,6 +131,10 @@ int launch_attention_tc(const void* qkv, bool f16, int batch, int tokens, int he
 // second-generation tcgen05 attention (attention_wb.cu): 0 = launched, 1 = shape not covered, <0 = error
 int launch_attention_wb(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out,
                         cudaStream_t stream);
+// attention of ONE query row per image (the class token, row 0) over all keys: out[b, head*dh ...] of a compact [B, D]
+// matrix with row stride ld_out elements (last layer of a class-token-pooled tower, tower.cu cls tail)
+int launch_attention_cls(const void* qkv, bool f16, int batch, int tokens, int heads, int head_dim, void* out, int ld_out,
+                         cudaStream_t stream);
 int launch_im2col(const void* pixels, int pix_fmt, int batch, int image_size, int patch, const float* mean3,
                   const float* std3, void* out, int kpad, bool out_f16, cudaStream_t stream);
 int launch_fill_cls(const float* cls_pos0, float* h, int batch, int tokens, int dim, cudaStream_t stream);

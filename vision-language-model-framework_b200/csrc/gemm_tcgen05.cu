@@ -92,7 +92,7 @@ struct KParams {
     // and the mean subtraction (rows centred: x (I - 11^T/K) W'^T == x (W' - rowmean(W'))^T), rstd comes from the
     // (sum, sum of squares) partials the producer of A's fp32 source left in ln_stats
     const float2* ln_stats;
-    int ln_np;
+    int ln_np, ln_row_mul;
     float ln_inv_dim, ln_eps;
     // ... and its producer side (residual epilogue): 16-bit copy of the updated rows through tmap_h16 and per-row
     // (sum, sum of squares) over this warp's 128 / 96 / 64 columns at stats_out[row * stats_np + 2 * n_tile + half]
@@ -322,7 +322,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 // folded LayerNorm: this thread's row statistics from the producer's partial sums (fixed order)
                 float mu = 0.f, rstd = 1.f;
                 if (p.ln_stats != nullptr && m0 + lane < p.m) {
-                    const float2* sp = p.ln_stats + static_cast<size_t>(m0 + lane) * p.ln_np;
+                    const float2* sp = p.ln_stats + static_cast<size_t>(m0 + lane) * p.ln_row_mul * p.ln_np;
                     float s1 = 0.f, s2 = 0.f;
                     for (int i = 0; i < p.ln_np; ++i) {
                         const float2 t = __ldg(sp + i);
@@ -868,6 +868,7 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
     p.grp_off = g.grp_off;
     p.ln_stats = reinterpret_cast<const float2*>(g.ln_stats);
     p.ln_np = g.ln_np;
+    p.ln_row_mul = g.ln_row_mul > 0 ? g.ln_row_mul : 1;
     p.ln_inv_dim = g.ln_dim > 0 ? 1.0f / static_cast<float>(g.ln_dim) : 0.f;
     p.ln_eps = g.ln_eps;
     p.stats_out = reinterpret_cast<float2*>(g.stats_out);

@@ -8,6 +8,8 @@
 //                          ignore_index=-1, :105-108) + base_trainer.py:166-181 (backward, AdamW step), split into
 //                          phases with plain-sum outputs so that a data-parallel caller can all-reduce them and land
 //                          on exactly the single-process result for the concatenated batch.
+#include <cstring>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -88,14 +90,96 @@ __global__ void __launch_bounds__(256) probe_forward_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ train step
+// Data-parallel exchange over NVLink peer memory, fused into the step's own kernels (vlmfw_comm below). Every rank owns one
+// exchange buffer [stats slots [world][2D] x 16 B | bucket slots [world][NB] x 8 B] that all peers have mapped (cudaIpc).
+// Every value travels WITH its flag in one store (the scheme NCCL calls LL): a bucket float goes as the 8-byte pair
+// {bits, epoch + 1}, a BatchNorm sum as the 16-byte quad {lo, epoch + 1, hi, epoch + 1} — 8-byte aligned stores are
+// single-copy atomic, over NVLink too, so a reader that sees the flag of this exchange sees the value that came with it. A
+// producer kernel writes its rank's contribution into slot `rank` of EVERY rank's buffer (plain stores to peer addresses);
+// the consumer thread of an element polls its LOCAL slots until each carries this exchange's flag and adds them in rank
+// order — the same order on every rank, so all replicas stay bit-identical. No fence, no separate flag, no collective
+// kernel: the cost of an exchange is one NVLink store latency (the first version — plain stores, fence.sys, one flag per
+// CTA per peer — paid two system-scope fences per producer CTA: 16 us per step on ONE rank; the two dependent
+// ncclAllReduce launches this replaces cost 21 us of a 96 us step at two ranks). epoch = exchanges completed through this
+// communicator, a device-side counter the step's last kernel advances, so flags never repeat and nothing is reset.
+// Slot reuse is safe without further handshakes: a rank reaches bn_stats of step t + 1 only after its AdamW of step t has
+// seen every rank's backward of step t, which those ranks launched after their own consumers of the step-t statistics.
+constexpr int DP_MAX_WORLD = 8;
+struct DpLink {
+    int world = 1, rank = 0;
+    uint4* stats[DP_MAX_WORLD];   // stats[r] = rank r's stats slots [world][2D] as mapped here
+    uint2* bucket[DP_MAX_WORLD];  // bucket[r] = rank r's bucket slots [world][NB]
+    const int64_t* epoch = nullptr;  // exchanges completed so far through this communicator (NOT the optimiser's step
+                                     // count, which the host may reset between graph replays)
+    int* error = nullptr;            // set to 1 when a poll ran out of patience (a peer died): the step's result is invalid
+};
+constexpr long long DP_SPIN_LIMIT = 1ll << 24;  // ~ seconds of polling
+
+__device__ __forceinline__ uint32_t dp_flag(const DpLink& lk) { return static_cast<uint32_t>(*lk.epoch + 1); }
+__device__ __forceinline__ void dp_put_f32(const DpLink& lk, size_t at, int nb, float t, uint32_t flag) {
+    const uint2 v = make_uint2(__float_as_uint(t), flag);
+    for (int r = 0; r < lk.world; ++r) {
+        uint2* dst = lk.bucket[r] + static_cast<size_t>(lk.rank) * nb + at;
+        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(v.x), "r"(v.y) : "memory");
+    }
+}
+__device__ __forceinline__ void dp_put_f64(const DpLink& lk, size_t at, int len, double t, uint32_t flag) {
+    const uint64_t bits = static_cast<uint64_t>(__double_as_longlong(t));
+    const uint32_t lo = static_cast<uint32_t>(bits), hi = static_cast<uint32_t>(bits >> 32);
+    for (int r = 0; r < lk.world; ++r) {
+        uint4* dst = lk.stats[r] + static_cast<size_t>(lk.rank) * len + at;
+        asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(flag), "r"(hi), "r"(flag)
+                     : "memory");
+    }
+}
+// sum over ranks (rank order) of element `at` of this rank's bucket / stats slots, each polled until it carries `flag`
+__device__ __forceinline__ float dp_get_f32(const DpLink& lk, size_t at, int nb, uint32_t flag) {
+    float t = 0.f;
+    for (int r = 0; r < lk.world; ++r) {
+        const uint2* src = lk.bucket[lk.rank] + static_cast<size_t>(r) * nb + at;
+        uint32_t x, f;
+        long long spins = 0;
+        do {
+            asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(f) : "l"(src) : "memory");
+            if (f != flag && ++spins > DP_SPIN_LIMIT) {
+                *lk.error = 1;
+                break;
+            }
+        } while (f != flag);
+        t += __uint_as_float(x);
+    }
+    return t;
+}
+__device__ __forceinline__ double dp_get_f64(const DpLink& lk, size_t at, int len, uint32_t flag) {
+    double t = 0.0;
+    for (int r = 0; r < lk.world; ++r) {
+        const uint4* src = lk.stats[lk.rank] + static_cast<size_t>(r) * len + at;
+        uint32_t lo, f0, hi, f1;
+        long long spins = 0;
+        do {
+            asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1)
+                         : "l"(src)
+                         : "memory");
+            if ((f0 != flag || f1 != flag) && ++spins > DP_SPIN_LIMIT) {
+                *lk.error = 1;
+                break;
+            }
+        } while (f0 != flag || f1 != flag);
+        t += __longlong_as_double(static_cast<long long>((static_cast<uint64_t>(hi) << 32) | lo));
+    }
+    return t;
+}
+
 // stats[d] = sum_b x[b,d], stats[dim+d] = sum_b x[b,d]^2 in fp64 (the variance is a difference of these).
 // A block owns 32 feature columns (lane = column: every warp load is one 128-byte line); its STAT_WARPS warps deal the
 // rows round-robin and their partials are combined in warp order through shared memory — a fixed summation order, so
 // the result does not depend on scheduling. (The first version ran ONE thread per column over all rows on 9 blocks:
 // a 256-deep chain of dependent L2 round trips, ~20x the time of everything else in the step.)
 constexpr int STAT_WARPS = 16;
+template <bool DP>
 __global__ void __launch_bounds__(32 * STAT_WARPS) bn_stats_kernel(const float* __restrict__ x, int batch, int dim,
-                                                                   double* __restrict__ stats) {
+                                                                   double* __restrict__ stats, const DpLink lk) {
     __shared__ double ss[STAT_WARPS][32];
     __shared__ double sq[STAT_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -119,9 +203,23 @@ __global__ void __launch_bounds__(32 * STAT_WARPS) bn_stats_kernel(const float* 
             st += ss[w][lane];
             qt += sq[w][lane];
         }
-        stats[d] = st;
-        stats[dim + d] = qt;
+        if constexpr (DP) {
+            // this rank's sums into slot `rank` of every rank's buffer (its own included: the consumer adds all slots)
+            const uint32_t flag = dp_flag(lk);
+            dp_put_f64(lk, d, 2 * dim, st, flag);
+            dp_put_f64(lk, dim + d, 2 * dim, qt, flag);
+        } else {
+            stats[d] = st;
+            stats[dim + d] = qt;
+        }
     }
+}
+
+// DP: global statistics = sum over ranks of the slots, in rank order, once per step (fused into the head of the dropout-mask
+// kernel's grid)
+__device__ __forceinline__ void dp_combine_stats(const DpLink& lk, int dim, double* __restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * dim) stats[i] = dp_get_f64(lk, i, 2 * dim, dp_flag(lk));
 }
 
 struct TrainArgs {
@@ -205,7 +303,18 @@ __global__ void __launch_bounds__(256) probe_train_fwd_kernel(TrainArgs a) {
 // per-warp partial sums of (dW[c][d], dgamma[d], dbeta[d]) meet in shared memory and are added in warp order — fixed
 // summation order, deterministic. bucket = [dW (C*D) | db (C) | dgamma (D) | dbeta (D) | loss_sum | weight_sum]
 constexpr int BWD_WARPS = 8;
-__global__ void __launch_bounds__(32 * BWD_WARPS) probe_train_bwd_kernel(TrainArgs a) {
+template <bool DP>
+__global__ void __launch_bounds__(32 * BWD_WARPS) probe_train_bwd_kernel(TrainArgs a, const DpLink lk, int nb) {
+    // DP: every bucket element goes to slot `rank` of every rank's exchange buffer instead of a.bucket
+    uint32_t flag = 0;
+    if constexpr (DP) flag = dp_flag(lk);
+    auto put = [&](size_t at, float t) {
+        if constexpr (DP) {
+            dp_put_f32(lk, at, nb, t, flag);
+        } else {
+            a.bucket[at] = t;
+        }
+    };
     extern __shared__ float bsm[];  // dlogits [B*C] | partials [BWD_WARPS][C + 2][32]
     const int nd = a.batch * a.classes;
     for (int i = threadIdx.x; i < nd; i += blockDim.x) bsm[i] = a.scratch[i];
@@ -262,7 +371,7 @@ __global__ void __launch_bounds__(32 * BWD_WARPS) probe_train_bwd_kernel(TrainAr
             for (int w = 0; w < BWD_WARPS; ++w) t += part[(static_cast<size_t>(w) * (C + 2) + k) * 32 + lane];
             const size_t at = k < C ? static_cast<size_t>(k) * D + d
                                     : static_cast<size_t>(C) * D + C + static_cast<size_t>(k - C) * D + d;
-            a.bucket[at] = t;
+            put(at, t);
         }
     }
     if (blockIdx.x == 0) {
@@ -273,7 +382,7 @@ __global__ void __launch_bounds__(32 * BWD_WARPS) probe_train_bwd_kernel(TrainAr
             float t = 0.f;
             for (int b = lane; b < a.batch; b += 32) t += k < C ? bsm[b * C + k] : (k == C ? loss_b[b] : w_b[b]);
             t = warp_sum(t);
-            if (lane == 0) a.bucket[static_cast<size_t>(C) * D + (k < C ? k : C + 2 * D + (k - C))] = t;
+            if (lane == 0) put(static_cast<size_t>(C) * D + (k < C ? k : C + 2 * D + (k - C)), t);
         }
     }
 }
@@ -283,7 +392,10 @@ __device__ __forceinline__ void adamw_body(float* __restrict__ p, float* __restr
                                            const float* __restrict__ bucket, int64_t numel, int64_t wsum_index, float lr,
                                            float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt) {
     const float wsum = bucket[wsum_index];
-    const float inv = wsum > 0.f ? 1.f / wsum : 0.f;
+    // every target of the (global) batch ignored: the reference's mean loss is 0/0 and its step poisons the head with NaN;
+    // here the step is skipped (no decay, no moment update), like the multitask path (probe_deep.cu adamw_ex_kernel)
+    if (!(wsum > 0.f)) return;
+    const float inv = 1.f / wsum;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < numel;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const float g = bucket[i] * inv;
@@ -318,7 +430,42 @@ __global__ void __launch_bounds__(256) adamw_dev_kernel(float* __restrict__ p, f
     adamw_body(p, m, v, bucket, numel, wsum_index, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
 }
 
+// DP form: the gradient bucket is the sum over ranks of this rank's slots (rank order: bit-identical on every rank); block 0
+// also leaves the all-reduced [loss_sum, weight_sum] in `bucket_out` for the host's loss read-back. `per_step` = CTAs of
+// probe_train_bwd_kernel.
+__global__ void __launch_bounds__(256) adamw_dp_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                       const DpLink lk, int nb, float* __restrict__ bucket_out,
+                                                       int64_t numel, int64_t wsum_index,
+                                                       const int64_t* __restrict__ steps_done, float lr, float beta1,
+                                                       float beta2, float eps, float wd) {
+    const uint32_t flag = dp_flag(lk);
+    auto total = [&](int64_t i) { return dp_get_f32(lk, static_cast<size_t>(i), nb, flag); };
+    const float step = static_cast<float>(*steps_done + 1);
+    const float bc1 = 1.f - powf(beta1, step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
+    const float wsum = total(wsum_index);
+    if (blockIdx.x == 0 && threadIdx.x < 2) bucket_out[numel + threadIdx.x] = total(numel + threadIdx.x);
+    if (!(wsum > 0.f)) return;  // all targets ignored: skip the update (see adamw_body)
+    const float inv = 1.f / wsum;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < numel;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float g = total(i) * inv;
+        float pi = p[i] * (1.f - lr * wd);
+        const float mi = beta1 * m[i] + (1.f - beta1) * g;
+        const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi -= (lr / bc1) * (mi / denom);
+        p[i] = pi;
+    }
+}
+
 __global__ void counter_add_kernel(int64_t* ctr, int64_t inc) { *ctr += inc; }
+__global__ void counter_add2_kernel(int64_t* a, int64_t* b) {
+    *a += 1;
+    *b += 1;
+}
 
 // running_mean/var <- (1-momentum) * old + momentum * batch stat (unbiased variance), nn.BatchNorm1d train mode
 __global__ void bn_running_kernel(float* __restrict__ rm, float* __restrict__ rv, const double* __restrict__ stats,
@@ -373,7 +520,7 @@ extern "C" int vlmfw_probe_bn_stats(const float* x, int32_t batch, int32_t dim, 
     VLMFW_REQUIRE(x && stats && batch > 0 && dim > 0, "probe_bn_stats: bad arguments");
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
-    bn_stats_kernel<<<(dim + 31) / 32, 32 * STAT_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(x, batch, dim, stats);
+    bn_stats_kernel<false><<<(dim + 31) / 32, 32 * STAT_WARPS, 0, static_cast<cudaStream_t>(stream)>>>(x, batch, dim, stats, DpLink());
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
@@ -417,8 +564,8 @@ extern "C" int vlmfw_probe_linear_grads(const float* x, const int64_t* targets, 
     const size_t bwd_smem = (((static_cast<size_t>(batch) * classes + 31) & ~static_cast<size_t>(31)) +
                              static_cast<size_t>(BWD_WARPS) * (classes + 2) * 32) * sizeof(float);
     static std::atomic<uint64_t> bwd_opt_in{0};  // one bit per device
-    VLMFW_CUDA_OK(ensure_dynamic_smem(probe_train_bwd_kernel, 96 * 1024, bwd_opt_in));
-    probe_train_bwd_kernel<<<(dim + 31) / 32, 32 * BWD_WARPS, bwd_smem, s>>>(a);
+    VLMFW_CUDA_OK(ensure_dynamic_smem(probe_train_bwd_kernel<false>, 96 * 1024, bwd_opt_in));
+    probe_train_bwd_kernel<false><<<(dim + 31) / 32, 32 * BWD_WARPS, bwd_smem, s>>>(a, DpLink(), 0);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
@@ -487,8 +634,15 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
-__global__ void dropout_mask_kernel(uint8_t* __restrict__ out, int64_t total, int32_t cols, int64_t row0, uint64_t key,
-                                    uint32_t threshold, const int64_t* __restrict__ steps_done, uint64_t step_stride) {
+// DP = true: the grid's first ceil(2 dim / 256) blocks also combine the ranks' BatchNorm sums (dp_combine_stats) — the mask
+// does not depend on them, the kernels behind it do, so the exchange's consumer side costs no launch of its own.
+template <bool DP>
+__global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ out, int64_t total, int32_t cols, int64_t row0, uint64_t key,
+                                    uint32_t threshold, const int64_t* __restrict__ steps_done, uint64_t step_stride,
+                                    const DpLink lk, int dim, double* __restrict__ stats) {
+    if constexpr (DP) {
+        if (static_cast<int>(blockIdx.x) * 256 < 2 * dim) dp_combine_stats(lk, dim, stats);
+    }
     const int64_t first = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 16;
     if (first >= total) return;
     const uint64_t base = static_cast<uint64_t>(row0) * static_cast<uint64_t>(cols) + static_cast<uint64_t>(first);
@@ -521,8 +675,8 @@ static int dropout_keep_mask_launch(uint8_t* keep, int32_t rows, int32_t cols, i
     const double t = static_cast<double>(dropout_p) * 4294967296.0;
     const uint32_t threshold = t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
     const int64_t threads = (total + 15) / 16;
-    dropout_mask_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        keep, total, cols, row0, key, threshold, steps_done, step_stride);
+    dropout_mask_kernel<false><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        keep, total, cols, row0, key, threshold, steps_done, step_stride, DpLink(), 0, nullptr);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
@@ -537,4 +691,177 @@ extern "C" int vlmfw_dropout_keep_mask_dev(uint8_t* keep, int32_t rows, int32_t 
                                            void* stream) {
     VLMFW_REQUIRE(steps_done, "dropout_keep_mask_dev: steps_done is null");
     return dropout_keep_mask_launch(keep, rows, cols, row0, key, steps_done, step_stride, dropout_p, stream);
+}
+
+
+// ------------------------------------------------------------------------------------------------ NVLink peer exchange
+// One exchange buffer per rank (cudaMalloc, exported with cudaIpc and mapped by every peer of the node):
+//   [256-byte header (unused) | stats slots [world][2D] x {lo, flag, hi, flag} | bucket slots [world][NB] x {bits, flag}]
+struct vlmfw_comm {
+    int rank = 0, world = 1;
+    int64_t stats_len = 0, bucket_len = 0;  // 2D doubles / NB floats per slot
+    size_t stats_off = 0, bucket_off = 0, bytes = 0;
+    uint8_t* local = nullptr;
+    uint8_t* peer[DP_MAX_WORLD] = {};
+    int* error_dev = nullptr;
+    int64_t* epoch_dev = nullptr;  // exchanges completed (see DpLink::epoch)
+    bool connected = false;
+};
+
+extern "C" int vlmfw_comm_create(int32_t rank, int32_t world, int64_t stats_doubles, int64_t bucket_floats, vlmfw_comm** out) {
+    VLMFW_REQUIRE(out && world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, "comm_create: rank %d / world %d (max %d ranks)",
+                  rank, world, DP_MAX_WORLD);
+    VLMFW_REQUIRE(stats_doubles > 0 && bucket_floats > 0, "comm_create: empty slots");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    vlmfw_comm* c = new vlmfw_comm();
+    c->rank = rank;
+    c->world = world;
+    c->stats_len = stats_doubles;
+    c->bucket_len = bucket_floats;
+    c->stats_off = 256;
+    c->bucket_off = c->stats_off + static_cast<size_t>(world) * stats_doubles * 16;  // {lo, flag, hi, flag} per double
+    c->bucket_off = (c->bucket_off + 255) / 256 * 256;
+    c->bytes = c->bucket_off + static_cast<size_t>(world) * bucket_floats * 8;  // {bits, flag} per float
+    if (cudaMalloc(reinterpret_cast<void**>(&c->local), c->bytes) != cudaSuccess ||
+        cudaMemset(c->local, 0, c->bytes) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&c->error_dev), 16) != cudaSuccess ||  // [int error | pad | int64 epoch]
+        cudaMemset(c->error_dev, 0, 16) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        set_error("comm_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (c->local) cudaFree(c->local);
+        if (c->error_dev) cudaFree(c->error_dev);
+        delete c;
+        return VLMFW_E_CUDA;
+    }
+    c->epoch_dev = reinterpret_cast<int64_t*>(c->error_dev + 2);
+    c->peer[rank] = c->local;
+    c->connected = world == 1;
+    *out = c;
+    return VLMFW_OK;
+}
+
+extern "C" int32_t vlmfw_comm_handle_bytes(void) { return static_cast<int32_t>(sizeof(cudaIpcMemHandle_t)); }
+
+extern "C" int vlmfw_comm_handle(vlmfw_comm* c, void* handle_out) {
+    VLMFW_REQUIRE(c && handle_out, "comm_handle: null argument");
+    cudaIpcMemHandle_t h;
+    VLMFW_CUDA_OK(cudaIpcGetMemHandle(&h, c->local));
+    memcpy(handle_out, &h, sizeof(h));
+    return VLMFW_OK;
+}
+
+// handles: world x vlmfw_comm_handle_bytes() bytes, entry r = rank r's handle (this rank's own entry is ignored)
+extern "C" int vlmfw_comm_connect(vlmfw_comm* c, const void* handles) {
+    VLMFW_REQUIRE(c && handles, "comm_connect: null argument");
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank || c->peer[r] != nullptr) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const uint8_t*>(handles) + static_cast<size_t>(r) * sizeof(h), sizeof(h));
+        void* ptr = nullptr;
+        VLMFW_CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer[r] = static_cast<uint8_t*>(ptr);
+    }
+    c->connected = true;
+    return VLMFW_OK;
+}
+
+extern "C" void vlmfw_comm_destroy(vlmfw_comm* c) {
+    if (!c) return;
+    for (int r = 0; r < c->world; ++r)
+        if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    if (c->local) cudaFree(c->local);
+    if (c->error_dev) cudaFree(c->error_dev);
+    delete c;
+}
+
+// 1 when a wait of some step gave up (a peer stopped reporting): every result since is invalid. Synchronises the device.
+extern "C" int vlmfw_comm_error(vlmfw_comm* c, int32_t* host_flag) {
+    VLMFW_REQUIRE(c && host_flag, "comm_error: null argument");
+    int v = 0;
+    VLMFW_CUDA_OK(cudaMemcpy(&v, c->error_dev, sizeof(int), cudaMemcpyDeviceToHost));
+    *host_flag = v;
+    return VLMFW_OK;
+}
+
+// One whole optimisation step of the linear head (bn_stats -> dropout mask -> forward -> backward -> AdamW -> BatchNorm
+// running statistics -> step counter) with the data-parallel exchange fused into its kernels. Seven launches, no collective
+// kernel; graph-capturable (everything that changes per step is read from *steps_done). With comm->world == 1 the arithmetic is
+// that of the separate entry points above.
+extern "C" int vlmfw_probe_linear_step_dp(const vlmfw_probe_step* a, vlmfw_comm* c, void* stream) {
+    VLMFW_REQUIRE(a && c, "probe_linear_step_dp: null argument");
+    VLMFW_REQUIRE(c->connected, "probe_linear_step_dp: vlmfw_comm_connect has not been called");
+    VLMFW_REQUIRE(a->x && a->targets && a->stats && a->params && a->exp_avg && a->exp_avg_sq && a->bucket && a->logits &&
+                      a->scratch && a->running_mean && a->running_var && a->steps_done,
+                  "probe_linear_step_dp: null pointer");
+    const int B = a->batch, D = a->dim, C = a->classes;
+    VLMFW_REQUIRE(B > 0 && D > 0 && C > 0 && C <= MAX_CLASSES && a->n_global >= B, "probe_linear_step_dp: bad shape");
+    VLMFW_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "probe_linear_step_dp: dropout_p out of range");
+    VLMFW_REQUIRE(a->dropout_p == 0.f || a->keep != nullptr, "probe_linear_step_dp: dropout needs a keep-mask buffer");
+    VLMFW_REQUIRE(static_cast<size_t>(B) * C * sizeof(float) <= 48 * 1024, "probe_linear_step_dp: batch*classes too large for one launch");
+    const int64_t n_params = static_cast<int64_t>(C) * D + C + 2 * D;
+    VLMFW_REQUIRE(c->stats_len == 2 * D && c->bucket_len == n_params + 2, "probe_linear_step_dp: the communicator was created for other sizes");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DpLink lk;
+    lk.world = c->world;
+    lk.rank = c->rank;
+    for (int r = 0; r < c->world; ++r) {
+        lk.stats[r] = reinterpret_cast<uint4*>(c->peer[r] + c->stats_off);
+        lk.bucket[r] = reinterpret_cast<uint2*>(c->peer[r] + c->bucket_off);
+    }
+    lk.epoch = c->epoch_dev;
+    lk.error = c->error_dev;
+    const int nb = static_cast<int>(n_params + 2);
+    const unsigned stat_ctas = static_cast<unsigned>((D + 31) / 32), bwd_ctas = stat_ctas;
+
+    bn_stats_kernel<true><<<stat_ctas, 32 * STAT_WARPS, 0, s>>>(a->x, B, D, a->stats, lk);
+    VLMFW_LAUNCH_CHECK();
+    {
+        const int64_t total = a->dropout_p > 0.f ? static_cast<int64_t>(B) * D : 0;
+        const double t = static_cast<double>(a->dropout_p) * 4294967296.0;
+        const uint32_t threshold = t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
+        int64_t blocks = ((total + 15) / 16 + 255) / 256;
+        const int64_t comb = (2 * D + 255) / 256;
+        if (blocks < comb) blocks = comb;
+        dropout_mask_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(a->keep, total, D, a->row0, a->mask_key, threshold,
+                                                                              a->steps_done, a->mask_step_stride, lk, D, a->stats);
+        VLMFW_LAUNCH_CHECK();
+    }
+    TrainArgs ta;
+    ta.x = a->x;
+    ta.targets = a->targets;
+    ta.batch = B;
+    ta.dim = D;
+    ta.classes = C;
+    ta.stats = a->stats;
+    ta.n_global = a->n_global;
+    ta.bn_eps = a->bn_eps;
+    ta.weight = a->params;
+    ta.bias = a->params + static_cast<size_t>(C) * D;
+    ta.gamma = ta.bias + C;
+    ta.beta = ta.gamma + D;
+    ta.class_weight = a->class_weight;
+    ta.keep = a->dropout_p > 0.f ? a->keep : nullptr;
+    ta.keep_scale = 1.f / (1.f - a->dropout_p);
+    ta.bucket = a->bucket;
+    ta.logits = a->logits;
+    ta.scratch = a->scratch;
+    probe_train_fwd_kernel<<<B, 256, static_cast<size_t>(D + C) * sizeof(float), s>>>(ta);
+    VLMFW_LAUNCH_CHECK();
+    const size_t bwd_smem = (((static_cast<size_t>(B) * C + 31) & ~static_cast<size_t>(31)) + static_cast<size_t>(BWD_WARPS) * (C + 2) * 32) * sizeof(float);
+    static std::atomic<uint64_t> bwd_opt_in{0};
+    VLMFW_CUDA_OK(ensure_dynamic_smem(probe_train_bwd_kernel<true>, 96 * 1024, bwd_opt_in));
+    probe_train_bwd_kernel<true><<<bwd_ctas, 32 * BWD_WARPS, bwd_smem, s>>>(ta, lk, nb);
+    VLMFW_LAUNCH_CHECK();
+    int grid = static_cast<int>((n_params + 255) / 256);
+    if (grid > 1024) grid = 1024;
+    adamw_dp_kernel<<<grid, 256, 0, s>>>(a->params, a->exp_avg, a->exp_avg_sq, lk, nb, a->bucket, n_params, n_params + 1, a->steps_done, a->lr,
+                                         a->beta1, a->beta2, a->eps, a->weight_decay);
+    VLMFW_LAUNCH_CHECK();
+    bn_running_kernel<<<(D + 127) / 128, 128, 0, s>>>(a->running_mean, a->running_var, a->stats, D, a->n_global, a->bn_momentum);
+    VLMFW_LAUNCH_CHECK();
+    counter_add2_kernel<<<1, 1, 0, s>>>(a->steps_done, c->epoch_dev);  // optimiser step count and exchange epoch
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
 }

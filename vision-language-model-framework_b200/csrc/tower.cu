@@ -143,6 +143,11 @@ struct vlmfw_tower {
     // out-proj / fc2 epilogues, which put out-proj on the HBM roofline with an fp32 stream. bf16 towers (8-bit mantissa)
     // and VLMFW_RESIDUAL=32 keep the fp32 stream.
     bool resid16 = false;
+    // Class-token-pooled towers (VLMFW_POOL_CLS, VLMFW_POOL_LN_CLS_LN): the adapter keeps row 0 of every image only, so the
+    // LAST encoder layer needs K and V of all rows but Q, attention, out-proj and the MLP of the class-token rows alone:
+    // GEMMs with M = B over rows b*S (row stride S*D), one-query attention. Same result for the pooled features; the other
+    // rows of the final residual stream are left as the last layer found them (vlmfw_tower_set_cls_tail(t, 0) computes them).
+    bool cls_tail = false;
     float* patch_b = nullptr;
     float* cls = nullptr;
     float* pos = nullptr;  // [S, D]
@@ -224,6 +229,9 @@ extern "C" int vlmfw_tower_create(const vlmfw_tower_cfg* cfg, vlmfw_tower** out)
     {
         const char* e = getenv("VLMFW_RESIDUAL");
         t->resid16 = t->f16 && !(e != nullptr && atoi(e) == 32);
+        const char* c = getenv("VLMFW_CLS_TAIL");
+        t->cls_tail = cfg->has_cls && (cfg->pool == VLMFW_POOL_CLS || cfg->pool == VLMFW_POOL_LN_CLS_LN) &&
+                      !(c != nullptr && atoi(c) == 0);
     }
     const int g = cfg->image_size / cfg->patch_size;
     t->P = g * g;
@@ -361,6 +369,15 @@ extern "C" const void* vlmfw_tower_hidden16_ptr(const vlmfw_tower* t, void* work
     if (!t || !workspace || batch <= 0 || !t->resid16) return nullptr;
     return static_cast<const uint8_t*>(workspace) + t->off_xn(batch);
 }
+
+extern "C" int vlmfw_tower_set_cls_tail(vlmfw_tower* t, int32_t enable) {
+    VLMFW_REQUIRE(t, "tower_set_cls_tail: null tower");
+    const bool can = t->cfg.has_cls && (t->cfg.pool == VLMFW_POOL_CLS || t->cfg.pool == VLMFW_POOL_LN_CLS_LN);
+    VLMFW_REQUIRE(!enable || can, "tower_set_cls_tail: this tower's pooling reads more than the class token");
+    t->cls_tail = enable != 0;
+    return VLMFW_OK;
+}
+extern "C" int32_t vlmfw_tower_cls_tail(const vlmfw_tower* t) { return t && t->cls_tail ? 1 : 0; }
 
 extern "C" int vlmfw_tower_saturation(vlmfw_tower* t, int64_t* host_count, int32_t reset, void* stream) {
     VLMFW_REQUIRE(t && host_count, "tower_saturation: null argument");
@@ -523,30 +540,60 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
     }
     for (int li = 0; li < t->L; ++li) {
         const LayerW& w = t->layers[li];
+        // last layer of a class-token-pooled tower: only rows b*S go past the K / V projection (see cls_tail)
+        const bool tail = t->cls_tail && li + 1 == t->L;
+        const int rows = tail ? batch : M;          // GEMM rows after attention
+        const int ld_rows = tail ? S * D : D;       // row stride of those rows in xn / h
         GemmArgs g;
         g.a = xn;
         g.lda = D;
-        g.w = w.wqkv;
         g.acc_scale = w.s_qkv;
         g.sat_count = t->f16 ? t->sat_dev : nullptr;
         g.f16 = t->f16;
         g.ldw = D;
-        g.m = M;
-        g.n = 3 * D;
         g.k = D;
-        g.bias = w.c2qkv;
         g.ln_stats = stats;
         g.ln_np = np;
         g.ln_dim = D;
         g.ln_eps = t->cfg.ln_eps;
         g.epi = VLMFW_EPI_BIAS_BF16;
         g.act = VLMFW_ACT_NONE;
-        g.out = qkv;
         g.ldo = 3 * D;
-        rc = launch_gemm(g, st);
-        if (rc != VLMFW_OK) return rc;
-        rc = launch_attention(qkv, t->f16, batch, S, t->H, t->dh, ctx, st);
-        if (rc != VLMFW_OK) return rc;
+        if (!tail) {
+            g.w = w.wqkv;
+            g.m = M;
+            g.n = 3 * D;
+            g.bias = w.c2qkv;
+            g.out = qkv;
+            rc = launch_gemm(g, st);
+            if (rc != VLMFW_OK) return rc;
+            rc = launch_attention(qkv, t->f16, batch, S, t->H, t->dh, ctx, st);
+            if (rc != VLMFW_OK) return rc;
+        } else {
+            // K | V of every row: weight rows [D, 3D), output columns [D, 3D)
+            GemmArgs kv = g;
+            kv.w = static_cast<const uint16_t*>(w.wqkv) + static_cast<size_t>(D) * D;
+            kv.m = M;
+            kv.n = 2 * D;
+            kv.bias = w.c2qkv + D;
+            kv.out = static_cast<uint16_t*>(qkv) + D;
+            rc = launch_gemm(kv, st);
+            if (rc != VLMFW_OK) return rc;
+            // Q of the class-token rows (row b of this GEMM = row b*S of xn / stats / qkv)
+            GemmArgs q = g;
+            q.lda = S * D;
+            q.ln_row_mul = S;
+            q.w = w.wqkv;
+            q.m = batch;
+            q.n = D;
+            q.bias = w.c2qkv;
+            q.out = qkv;
+            q.ldo = S * 3 * D;
+            rc = launch_gemm(q, st);
+            if (rc != VLMFW_OK) return rc;
+            rc = launch_attention_cls(qkv, t->f16, batch, S, t->H, t->dh, ctx, D, st);  // ctx rows 0..B-1, compact
+            if (rc != VLMFW_OK) return rc;
+        }
         g = GemmArgs();
         g.a = ctx;
         g.lda = D;
@@ -555,7 +602,7 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.sat_count = t->f16 ? t->sat_dev : nullptr;
         g.f16 = t->f16;
         g.ldw = D;
-        g.m = M;
+        g.m = rows;
         g.n = D;
         g.k = D;
         g.bias = w.bo;
@@ -568,22 +615,22 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
             g.out = h;
             g.resid = h;
             g.h16_out = xn;
-            g.ld_h16 = D;
+            g.ld_h16 = ld_rows;
         }
-        g.ldo = D;
-        g.ldr = D;
-        g.stats_out = stats;
+        g.ldo = ld_rows;
+        g.ldr = ld_rows;
+        g.stats_out = stats;  // tail: statistics rows 0..B-1 (compact), read back by fc1 below with the same indexing
         rc = launch_gemm(g, st);
         if (rc != VLMFW_OK) return rc;
         g = GemmArgs();
         g.a = xn;
-        g.lda = D;
+        g.lda = ld_rows;
         g.w = w.w1;
         g.acc_scale = w.s_fc1;
         g.sat_count = t->f16 ? t->sat_dev : nullptr;
         g.f16 = t->f16;
         g.ldw = D;
-        g.m = M;
+        g.m = rows;
         g.n = I;
         g.k = D;
         g.bias = w.c2fc1;
@@ -605,12 +652,12 @@ extern "C" int vlmfw_tower_forward(vlmfw_tower* t, const void* pixels, int32_t p
         g.sat_count = t->f16 ? t->sat_dev : nullptr;
         g.f16 = t->f16;
         g.ldw = t->Ild();
-        g.m = M;
+        g.m = rows;
         g.n = D;
         g.k = I;
         g.bias = w.b2;
-        g.ldo = D;
-        g.ldr = D;
+        g.ldo = ld_rows;
+        g.ldr = ld_rows;
         if (t->resid16) {
             g.epi = VLMFW_EPI_BIAS_RESID_16;
             g.out = xn;
@@ -766,6 +813,13 @@ extern "C" int vlmfw_attention(const void* qkv, int32_t dtype, int32_t batch, in
     VLMFW_REQUIRE(dtype == VLMFW_DT_BF16 || dtype == VLMFW_DT_F16, "attention: dtype must be VLMFW_DT_BF16 or VLMFW_DT_F16");
     return launch_attention(qkv, dtype == VLMFW_DT_F16, batch, tokens, heads, head_dim, out,
                             static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlmfw_attention_cls(const void* qkv, int32_t dtype, int32_t batch, int32_t tokens, int32_t heads,
+                                   int32_t head_dim, void* out, int32_t ld_out, void* stream) {
+    VLMFW_REQUIRE(dtype == VLMFW_DT_BF16 || dtype == VLMFW_DT_F16, "attention_cls: dtype must be VLMFW_DT_BF16 or VLMFW_DT_F16");
+    return launch_attention_cls(qkv, dtype == VLMFW_DT_F16, batch, tokens, heads, head_dim, out, ld_out,
+                                static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vlmfw_im2col(const void* pixels, int32_t pix_fmt, int32_t batch, int32_t image_size, int32_t patch_size,

@@ -94,6 +94,19 @@ class TowerEngine:
         """True when this tower's arithmetic is the one the parity tests hold to the north-star tolerance (fp16 operands)."""
         return self.compute_dtype == "f16"
 
+    @property
+    def cls_tail(self) -> bool:
+        """True when the last encoder layer runs for the class-token rows only (towers pooled from the class token: EVA's
+        ``pooler_output``, CLIP in "cls" mode). The pooled features do not change; ``hidden_state`` then holds final
+        values in row 0 of every image only."""
+        return bool(self._lib.vlmfw_tower_cls_tail(self._h))
+
+    def set_cls_tail(self, enable: bool) -> None:
+        """Switch the class-token-only last layer on / off (off: every row of the last layer is computed). Captured graphs
+        are dropped: the kernel sequence changes."""
+        _lib.check(self._lib.vlmfw_tower_set_cls_tail(self._h, int(bool(enable))))
+        self._graphs.clear()
+
     def saturation_count(self, reset: bool = False) -> int:
         """16-bit activation stores that clamped at +-65504 since creation / the last reset (0: no forward clipped).
         Synchronises the current stream."""

@@ -211,6 +211,20 @@ def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: 
     return out
 
 
+def attention_cls(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: int) -> torch.Tensor:
+    """Attention of query row 0 of every image over all keys: qkv as for ``attention`` -> [B, H*dh] in the same dtype."""
+    _need(qkv, qkv.dtype, "qkv")
+    dt = _dt(qkv, "qkv")
+    d = heads * head_dim
+    if tuple(qkv.shape) != (batch * tokens, 3 * d):
+        raise ValueError(f"qkv must be [{batch * tokens}, {3 * d}], got {tuple(qkv.shape)}")
+    out = torch.empty(batch, d, dtype=qkv.dtype, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.load().vlmfw_attention_cls(qkv.data_ptr(), dt, batch, tokens, heads, head_dim, out.data_ptr(), d,
+                                                   _st(qkv)))
+    return out
+
+
 def im2col(pixels: torch.Tensor, image_size: int, patch: int, kpad: int, mean: Sequence[float] = (0, 0, 0),
            std: Sequence[float] = (1, 1, 1), dtype: torch.dtype = torch.float16) -> torch.Tensor:
     if not pixels.is_cuda or not pixels.is_contiguous():

@@ -51,9 +51,12 @@ class ProbeTrainStep:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("ProbeTrainStep runs on CUDA only: vlmfw_b200 has no CPU fallback")
-        if comm not in ("auto", "nccl"):
-            raise ValueError("comm must be 'auto' or 'nccl'")
-        self.comm = "nccl"
+        if comm not in ("auto", "nccl", "p2p"):
+            raise ValueError("comm must be 'auto', 'nccl' or 'p2p'")
+        # exchange of the graph-form step: "p2p" = fused into the step's kernels over NVLink peer memory (vlmfw_comm, one node),
+        # "nccl" = two ncclAllReduce calls between the kernels; "auto" = p2p when a process group is up, else nothing to exchange
+        self.comm = comm
+        self._comm_h = None
         self.dim, self.classes = dim, classes
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.dropout_p, self.bn_eps, self.bn_momentum = dropout_p, bn_eps, bn_momentum
@@ -84,13 +87,24 @@ class ProbeTrainStep:
     # bn_running, counter_add (csrc/probe.cu); NCCL's all-reduce kernels are not counted
     kernels_per_step = 7
 
+    def _use_p2p(self) -> bool:
+        import torch.distributed as dist
+
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        return self.comm == "p2p" or (self.comm == "auto" and distributed)
+
     def exchange_description(self) -> str:
+        if self._comm_h is not None:
+            return ("fused into the step's kernels over NVLink peer memory: bn_stats / backward store their sums into every "
+                    "rank's slots and raise flags, the mask / AdamW kernels wait on local flags and add the slots in rank order "
+                    "(BatchNorm sums [2D] fp64, gradient bucket [C*D + C + 2D + 2] fp32); no collective kernel")
         return ("2 dependent NCCL all-reduces per step: BatchNorm batch sums [2D] fp64, then the flat gradient bucket "
                 "[C*D + C + 2D + 2] fp32")
 
     def exchange_report(self, steps: int = 200) -> dict:
-        """Latency of the step's exchange measured in isolation: ``steps`` DEPENDENT all-reduces of each of the two
-        buffers, captured in one CUDA graph like the train step, timed with CUDA events (max over ranks)."""
+        """Latency of the NCCL form of the exchange measured in isolation (the baseline the fused form replaces): ``steps``
+        DEPENDENT all-reduces of each of the two buffers, captured in one CUDA graph like the train step, timed with CUDA
+        events (max over ranks)."""
         import torch.distributed as dist
 
         dev = self.device
@@ -231,6 +245,9 @@ class ProbeTrainStep:
         self._g_steps_done_value = self.step_count
         self._g_loss = torch.zeros(2, dtype=torch.float32).pin_memory()
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if self._use_p2p():
+            self._capture_p2p(b_local, n_global, global_offset)
+            return
         if distributed:  # communicator set-up cannot be captured: run one collective of each dtype eagerly first
             allreduce_sum_(torch.zeros(2, dtype=torch.float64, device=dev), self.group)
             allreduce_sum_(torch.zeros(2, device=dev), self.group)
@@ -263,10 +280,72 @@ class ProbeTrainStep:
             self._g_loss.copy_(self.bucket[self.n_params:], non_blocking=True)
         self._graph = graph
 
+    def _capture_p2p(self, b_local: int, n_global: int, global_offset: int) -> None:
+        """Graph form of the step with the exchange fused into its kernels (vlmfw_probe_linear_step_dp): seven launches of
+        this library and nothing else. Communicator set-up: every rank allocates its exchange buffer, the cudaIpc handles go
+        round with one all_gather_object, every rank maps its peers' buffers."""
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        dev, d, c, lib = self.device, self.dim, self.classes, self._lib
+        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(self.group) if world > 1 else 0
+        with torch.cuda.device(dev):
+            h = C.c_void_p()
+            _lib.check(lib.vlmfw_comm_create(rank, world, 2 * d, self.n_params + 2, C.byref(h)))
+            self._comm_h = h
+            if world > 1:
+                nbytes = lib.vlmfw_comm_handle_bytes()
+                mine = (C.c_char * nbytes)()
+                _lib.check(lib.vlmfw_comm_handle(h, mine))
+                handles = [None] * world
+                dist.all_gather_object(handles, bytes(mine), group=self.group)
+                blob = b"".join(handles)
+                _lib.check(lib.vlmfw_comm_connect(h, blob))
+                dist.barrier(self.group)  # every rank has mapped every buffer before anybody stores into one
+        a = _lib.ProbeStep(
+            x=self._g_x.data_ptr(), targets=self._g_y.data_ptr(), batch=b_local, dim=d, classes=c, n_global=n_global,
+            row0=global_offset, stats=self.stats.data_ptr(), params=self.params.data_ptr(), exp_avg=self.exp_avg.data_ptr(),
+            exp_avg_sq=self.exp_avg_sq.data_ptr(), bucket=self.bucket.data_ptr(), logits=self._g_logits.data_ptr(),
+            scratch=self._g_scratch.data_ptr(), keep=None if self._g_keep is None else self._g_keep.data_ptr(),
+            class_weight=None if self.class_weight is None else self.class_weight.data_ptr(),
+            running_mean=self.running_mean.data_ptr(), running_var=self.running_var.data_ptr(),
+            steps_done=self._g_steps_done.data_ptr(), mask_key=mask_key(self.seed, 0), mask_step_stride=MASK_KEY_STEP_STRIDE,
+            dropout_p=float(self.dropout_p), bn_eps=float(self.bn_eps), bn_momentum=float(self.bn_momentum), lr=float(self.lr),
+            beta1=float(self.betas[0]), beta2=float(self.betas[1]), eps=float(self.eps), weight_decay=float(self.wd))
+        self._g_args = a
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(dev), torch.cuda.graph(graph):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.vlmfw_probe_linear_step_dp(C.byref(a), self._comm_h, st))
+            self._g_loss.copy_(self.bucket[self.n_params:], non_blocking=True)
+        self._graph = graph
+
+    def comm_error(self) -> bool:
+        """True when a wait of the fused exchange gave up (a peer stopped reporting): results since then are invalid."""
+        import ctypes as C
+
+        if self._comm_h is None:
+            return False
+        flag = C.c_int32(0)
+        _lib.check(self._lib.vlmfw_comm_error(self._comm_h, C.byref(flag)))
+        return bool(flag.value)
+
     def release_graph(self) -> None:
-        """Drop the captured graph (and with it the captured NCCL kernels). Call before
-        ``torch.distributed.destroy_process_group()``: tearing a communicator down under a live graph can block."""
+        """Drop the captured graph (and with it the captured NCCL kernels / the peer-memory communicator). Call before
+        ``torch.distributed.destroy_process_group()``: tearing a communicator down under a live graph can block. In a
+        process group every rank must call it (the peer buffers are unmapped behind a barrier)."""
+        import torch.distributed as dist
+
         self._graph = None
+        if self._comm_h is not None:
+            torch.cuda.synchronize(self.device)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                dist.barrier(self.group)  # nobody frees a buffer a peer may still be storing into
+            self._lib.vlmfw_comm_destroy(self._comm_h)
+            self._comm_h = None
 
     def step_graph(self, x: torch.Tensor, y: torch.Tensor) -> float:
         """``step`` through the captured graph: stage this rank's rows (host or device tensors) into the graph's input
