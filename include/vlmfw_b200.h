@@ -244,6 +244,11 @@ int vlmfw_probe_deep_grads(const float* x, const int64_t* targets, int32_t batch
 int vlmfw_probe_adamw_ex(float* params, float* exp_avg, float* exp_avg_sq, const float* bucket, int64_t numel,
                          int64_t weight_sum_index, float grad_scale, int32_t step, float lr, float beta1, float beta2,
                          float eps, float weight_decay, void* stream);
+/* the same update with the step number (*steps_done = optimisation steps completed so far) and the task weight (*grad_scale)
+ * read from device memory: nothing in the launch changes between steps, so a multitask step replays from one CUDA graph */
+int vlmfw_probe_adamw_ex_dev(float* params, float* exp_avg, float* exp_avg_sq, const float* bucket, int64_t numel,
+                             int64_t weight_sum_index, const float* grad_scale, const int64_t* steps_done, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, void* stream);
 int vlmfw_probe_bn_running_update(float* running_mean, float* running_var, const double* stats, int32_t dim,
                                   int32_t n_global, float momentum, void* stream);
 /* Dropout keep mask of the train-mode heads (nn.Dropout(p) in make_head / make_head_deeper,
@@ -269,11 +274,12 @@ int vlmfw_counter_add(int64_t* counter, int64_t inc, void* stream);
 /* Data-parallel exchange of the train step over NVLink peer memory, fused into the step's own kernels (BASELINE configs[4]:
  * "only the tiny probe-weight gradients are allreduced"; the reference itself has no multi-GPU training —
  * probing/train/base_trainer.py:30). One process per GPU of ONE node. Each rank creates a communicator (one exchange
- * buffer: flags + per-rank slots for the BatchNorm sums [2D] fp64 and the gradient bucket [C*D + C + 2D + 2] fp32), the host
+ * buffer: per-rank slots for the BatchNorm sums [2D] fp64 and the gradient bucket [C*D + C + 2D + 2] fp32), the host
  * exchanges the handles (vlmfw_comm_handle -> all-gather -> vlmfw_comm_connect maps every peer's buffer with cudaIpc), and
  * vlmfw_probe_linear_step_dp then runs whole optimisation steps: the producing kernels store their rank's sums straight into
- * every peer's slots and raise per-CTA flags, the consuming kernels wait on their local flags and add the slots in rank
- * order (bit-identical parameters on all ranks). No collective kernel is launched. world == 1 needs no connect. */
+ * every peer's slots, every value together with the flag of this exchange in ONE 8-byte (fp32) / 16-byte (fp64) store; the
+ * consuming kernels poll their LOCAL slots until each carries the flag and add them in rank order (bit-identical parameters
+ * on all ranks). No fence, no separate flag, no collective kernel. world == 1 needs no connect. */
 typedef struct vlmfw_comm vlmfw_comm;
 int vlmfw_comm_create(int32_t rank, int32_t world, int64_t stats_doubles, int64_t bucket_floats, vlmfw_comm** out);
 int32_t vlmfw_comm_handle_bytes(void);

@@ -134,3 +134,53 @@ def test_unlabelled_task_is_left_untouched_and_ema_weights(cuda_device):
     assert ts.ema["a"] == pytest.approx(0.9 * first + 0.1 * l2["a"]) and ts.ema["b"] == pytest.approx(l2["b"])
     raw = [1 / ts.ema["a"], 1 / ts.ema["b"]]
     assert ts.on_epoch_start() == pytest.approx({"a": raw[0] / (sum(raw) / 2), "b": raw[1] / (sum(raw) / 2)})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,tasks,hidden,n,p", [(1024, MIVIA, 0, 128, 0.3), (1152, {"age": 9, "gender": 2}, 512, 256, 0.3),
+                                                  (144, {"gender": 2, "emotion": 7}, 64, 33, 0.0)])
+def test_multitask_graph_step_equals_eager_step(cuda_device, dim, tasks, hidden, n, p):
+    """The multitask / deeper step replayed from one CUDA graph (device-side step counter for the dropout keys and AdamW's
+    bias corrections, task weights in a device vector) = the eager step: same masks, same losses, same parameters; also
+    when the task weights change between steps (running means) and when eager and graph steps alternate."""
+    from vlmfw_b200.probe_train import MultiTaskProbeTrainStep
+
+    steps = 5
+    g = torch.Generator().manual_seed(3)
+    xs = [(torch.randn(n, dim, generator=g) * 1.2 + 0.1).cuda() for _ in range(steps)]
+    ys = [torch.stack([torch.randint(-1, c, (n,), generator=g) for c in tasks.values()], dim=1).cuda() for _ in range(steps)]
+
+    def fresh():
+        return MultiTaskProbeTrainStep(dim, tasks, "cuda", deeper=hidden > 0, hidden_dim=hidden, dropout_p=p, seed=4,
+                                       use_running_means=True, ema_alpha=0.8, lr=1e-3)
+
+    eager, graph, mixed = fresh(), fresh(), fresh()
+    graph.capture(n)
+    mixed.step(xs[0], ys[0])
+    mixed.capture(n)
+    with pytest.raises(ValueError):
+        graph.step_graph(xs[0][:5], ys[0][:5])
+    for s in range(steps):
+        if s == 2:  # epoch boundary: the task weights move to the inverse running means
+            for t in (eager, graph, mixed):
+                t.on_epoch_start()
+            assert graph.current_task_weights == pytest.approx(eager.current_task_weights)
+        le = eager.step(xs[s], ys[s])
+        lg = graph.step_graph(xs[s].cpu() if s % 2 else xs[s], ys[s])
+        for t in tasks:
+            assert (le[t] is None) == (lg[t] is None)
+            if le[t] is not None:
+                assert abs(le[t] - lg[t]) <= 2e-6 * max(1.0, abs(le[t])), (s, t, le[t], lg[t])
+        if s >= 1:
+            lm = mixed.step_graph(xs[s], ys[s]) if s % 2 else mixed.step(xs[s], ys[s])
+            for t in tasks:
+                if le[t] is not None:
+                    assert abs(le[t] - lm[t]) <= 2e-6 * max(1.0, abs(le[t]))
+    for other in (graph, mixed):
+        assert other.step_count == eager.step_count == steps
+        for t in tasks:
+            torch.testing.assert_close(other.heads[t].params, eager.heads[t].params, rtol=0, atol=5e-7)
+            torch.testing.assert_close(other.heads[t].running_var, eager.heads[t].running_var, rtol=1e-6, atol=1e-7)
+            assert other.heads[t].num_batches_tracked == eager.heads[t].num_batches_tracked
+            torch.testing.assert_close(other.last_logits[t], eager.last_logits[t], rtol=1e-5, atol=1e-6)
+        other.release_graph()

@@ -106,6 +106,7 @@ SIGNATURES = {
     "vlmfw_probe_deep_grads": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _f32,
                                          _vp, _vp, _vp, _vp]),
     "vlmfw_probe_adamw_ex": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _i32, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "vlmfw_probe_adamw_ex_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _vp]),
     "vlmfw_probe_bn_running_update": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, _vp]),
     "vlmfw_dropout_keep_mask": (C.c_int, [_vp, _i32, _i32, _i64, C.c_uint64, _f32, _vp]),
     "vlmfw_probe_adamw_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _f32, _f32, _f32, _f32, _f32, _vp]),

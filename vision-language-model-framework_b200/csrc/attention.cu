@@ -291,7 +291,9 @@ __global__ void __launch_bounds__(CLS_THREADS) attention_cls_kernel(const uint16
     const uint16_t* kb = base + dmodel + lane16 * 8;
     const uint16_t* vb = base + 2 * dmodel + lane16 * 8;
     // ---- scores (log2 domain)
-    for (int j0 = hw; j0 < tokens; j0 += 4 * CLS_HW) {
+    // (the trip count is the same for every thread: both half-warps of a warp take part in the full-mask shuffles below)
+    for (int base = 0; base < tokens; base += 4 * CLS_HW) {
+        const int j0 = base + hw;
         uint4 u[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -341,7 +343,8 @@ __global__ void __launch_bounds__(CLS_THREADS) attention_cls_kernel(const uint16
     for (int w = 0; w < CLS_THREADS / 32; ++w) sum += sred[8 + w];
     // ---- P.V: half-warp hw takes keys hw, hw + 16, ...; lane = chunk of 8 output columns
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int j0 = hw; j0 < tokens; j0 += 4 * CLS_HW) {
+    for (int base = 0; base < tokens; base += 4 * CLS_HW) {
+        const int j0 = base + hw;
         uint4 u[4];
         float pj[4];
 #pragma unroll

@@ -107,21 +107,26 @@ __device__ __forceinline__ const void* row_ptr(const void* base, size_t elems) {
 }
 
 // SigLIP: pooled[b, d] = mean_s ( (h[b,s,d] - mu_s) * rstd_s ) * gamma[d] + beta[d].
-// One CTA (1024 threads) per image. Phase 1: warps compute per-token (mu, rstd) into smem. Phase 2: thread d accumulates
-// its column over the tokens — the image's 1.2 MB was just read by phase 1, so this second pass is served by L2 and
-// HBM sees each row once (the first version used one CTA per 256-column slab, each recomputing every token's
-// statistics: 4x the algorithmic DRAM reads in the round-1 ncu capture).
+// One CTA (POOL_WARPS warps) per image, ONE pass: a warp owns a token at a time — row into registers, two-pass statistics in
+// registers, the normalised row added to the warp's own per-lane column accumulators — and the warps' accumulators meet in
+// shared memory, added in warp order (fixed summation order). Every row is read once, by one warp, straight from HBM. (The
+// previous version wrote per-token (mu, rstd) to shared memory and re-read the image column by column: served by L2 for the
+// 16-bit stream, but 2x the algorithmic DRAM bytes for the fp32 one in the round-1 ncu capture, and 94 us for 151 MB.)
+constexpr int POOL_WARPS = 16;
 template <int DT>
-__global__ void __launch_bounds__(1024) pool_ln_mean_kernel(const void* __restrict__ h, int tokens, int dim,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, float eps,
-                                                            float* __restrict__ pooled) {
-    extern __shared__ float2 stats[];  // [tokens] (mean, rstd)
+__global__ void __launch_bounds__(32 * POOL_WARPS) pool_ln_mean_kernel(const void* __restrict__ h, int tokens, int dim,
+                                                                       const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta, float eps,
+                                                                       float* __restrict__ pooled) {
+    extern __shared__ float4 pool_part[];  // [POOL_WARPS][dim / 4]
     const int b = blockIdx.x;
     const void* hb = row_ptr<DT>(h, static_cast<size_t>(b) * tokens * dim);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = dim >> 2;
-    for (int s = warp; s < tokens; s += nwarps) {
+    float4 acc[LN_MAX_CHUNKS];
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = warp; s < tokens; s += POOL_WARPS) {
         const void* xr = row_ptr<DT>(hb, static_cast<size_t>(s) * dim);
         float4 v[LN_MAX_CHUNKS];
         float sum = 0.f;
@@ -144,25 +149,42 @@ __global__ void __launch_bounds__(1024) pool_ln_mean_kernel(const void* __restri
             }
         }
         const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(dim) + eps);
-        if (lane == 0) stats[s] = make_float2(mean, rstd);
+#pragma unroll
+        for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+            const int c = i * 32 + lane;
+            if (c < nchunks) {
+                acc[i].x += (v[i].x - mean) * rstd;
+                acc[i].y += (v[i].y - mean) * rstd;
+                acc[i].z += (v[i].z - mean) * rstd;
+                acc[i].w += (v[i].w - mean) * rstd;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+        const int c = i * 32 + lane;
+        if (c < nchunks) pool_part[warp * nchunks + c] = acc[i];
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < dim; d += blockDim.x) {
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;  // four independent chains keep loads in flight
-        int s = 0;
-        for (; s + 4 <= tokens; s += 4) {
-            const float2 t0 = stats[s], t1 = stats[s + 1], t2 = stats[s + 2], t3 = stats[s + 3];
-            acc0 += (ld1<DT>(hb, static_cast<size_t>(s) * dim + d) - t0.x) * t0.y;
-            acc1 += (ld1<DT>(hb, static_cast<size_t>(s + 1) * dim + d) - t1.x) * t1.y;
-            acc2 += (ld1<DT>(hb, static_cast<size_t>(s + 2) * dim + d) - t2.x) * t2.y;
-            acc3 += (ld1<DT>(hb, static_cast<size_t>(s + 3) * dim + d) - t3.x) * t3.y;
+    const float inv_tokens = 1.f / static_cast<float>(tokens);
+    for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
+        float4 t = pool_part[c];
+#pragma unroll
+        for (int w = 1; w < POOL_WARPS; ++w) {
+            const float4 u = pool_part[w * nchunks + c];
+            t.x += u.x;
+            t.y += u.y;
+            t.z += u.z;
+            t.w += u.w;
         }
-        for (; s < tokens; ++s) {
-            const float2 st = stats[s];
-            acc0 += (ld1<DT>(hb, static_cast<size_t>(s) * dim + d) - st.x) * st.y;
-        }
-        const float acc = (acc0 + acc1) + (acc2 + acc3);
-        pooled[static_cast<size_t>(b) * dim + d] = acc / static_cast<float>(tokens) * gamma[d] + beta[d];
+        const float4 g = reinterpret_cast<const float4*>(gamma)[c];
+        const float4 bt = reinterpret_cast<const float4*>(beta)[c];
+        float4 o;
+        o.x = t.x * inv_tokens * g.x + bt.x;
+        o.y = t.y * inv_tokens * g.y + bt.y;
+        o.z = t.z * inv_tokens * g.z + bt.z;
+        o.w = t.w * inv_tokens * g.w + bt.w;
+        reinterpret_cast<float4*>(pooled + static_cast<size_t>(b) * dim)[c] = o;
     }
 }
 
@@ -397,9 +419,14 @@ static int launch_pool_t(const void* h, int batch, int tokens, int dim, int pool
     switch (pool) {
         case VLMFW_POOL_LN_MEAN:
             VLMFW_REQUIRE(gamma && beta, "pool: LN_MEAN needs gamma/beta");
-            VLMFW_REQUIRE(tokens * sizeof(float2) <= 48 * 1024, "pool: too many tokens %d", tokens);
-            pool_ln_mean_kernel<DT><<<batch, 1024, tokens * sizeof(float2), stream>>>(h, tokens, dim, gamma, beta, eps, pooled);
+        {
+            VLMFW_REQUIRE(dim % 4 == 0 && dim <= LN_MAX_CHUNKS * 128, "pool: LN_MEAN needs dim %% 4 == 0 and dim <= %d", LN_MAX_CHUNKS * 128);
+            const size_t smem = static_cast<size_t>(POOL_WARPS) * dim * sizeof(float);
+            static std::atomic<uint64_t> opt_in{0};  // per instantiation, one bit per device
+            VLMFW_CUDA_OK(ensure_dynamic_smem(pool_ln_mean_kernel<DT>, POOL_WARPS * LN_MAX_CHUNKS * 128 * 4, opt_in));
+            pool_ln_mean_kernel<DT><<<batch, 32 * POOL_WARPS, smem, stream>>>(h, tokens, dim, gamma, beta, eps, pooled);
             break;
+        }
         case VLMFW_POOL_MEAN:
             pool_mean_kernel<DT><<<grid, threads, 0, stream>>>(h, tokens, dim, tokens, pooled);
             break;

@@ -164,14 +164,53 @@ __global__ void __launch_bounds__(128) ce_kernel(float* __restrict__ logits, con
     w_b[b] = w;
 }
 
-// out[j] = sum_b src[b*ld + j] in row order (deterministic); one thread per column
-__global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ src, int rows, int cols, int ld,
-                                                     float* __restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cols) return;
+// Column sums over the batch rows. A block owns 32 columns (lane = column: a warp load is one 128-byte line of a row), its
+// RED_WARPS warps deal the rows round-robin and their partials meet in shared memory, added in warp order — a fixed
+// summation order, so the result does not depend on scheduling. (The first version ran one THREAD per column over all rows:
+// a 256-deep chain of dependent L2 round trips per launch, the pattern that cost the linear head 2x before probe.cu's
+// bn_stats / backward kernels were dealt the same way.)
+constexpr int RED_WARPS = 8;
+__global__ void __launch_bounds__(32 * RED_WARPS) colsum_kernel(const float* __restrict__ src, int rows, int cols, int ld,
+                                                                float* __restrict__ out) {
+    __shared__ float part[RED_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
     float s = 0.f;
-    for (int b = 0; b < rows; ++b) s += src[static_cast<size_t>(b) * ld + j];
-    out[j] = s;
+    if (j < cols)
+        for (int b = warp; b < rows; b += RED_WARPS) s += src[static_cast<size_t>(b) * ld + j];
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && j < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < RED_WARPS; ++w) t += part[w][lane];
+        out[j] = t;
+    }
+}
+
+// the three batch sums behind the cross entropy in one launch: db2[c] = sum_b dlog[b, c], tail = [sum_b loss_b, sum_b w_b];
+// column j < C reads dlog, column C the losses, column C + 1 the weights (grid = ceil((C + 2) / 32) blocks)
+__global__ void __launch_bounds__(32 * RED_WARPS) ce_sums_kernel(const float* __restrict__ dlog, const float* __restrict__ loss_b,
+                                                                 const float* __restrict__ w_b, int rows, int classes,
+                                                                 float* __restrict__ db2, float* __restrict__ tail) {
+    __shared__ float part[RED_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (j < classes + 2)
+        for (int b = warp; b < rows; b += RED_WARPS)
+            s += j < classes ? dlog[static_cast<size_t>(b) * classes + j] : (j == classes ? loss_b[b] : w_b[b]);
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && j < classes + 2) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < RED_WARPS; ++w) t += part[w][lane];
+        if (j < classes)
+            db2[j] = t;
+        else
+            tail[j - classes] = t;
+    }
 }
 
 // da = dz2 * keep2 * gelu'(a), in place over dz2
@@ -186,23 +225,37 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(float* __restrict__ dz2, 
     }
 }
 
-// dgamma[d] = sum_b dz1 keep1 xh, dbeta[d] = sum_b dz1 keep1 — one thread per feature column, rows in order
-__global__ void __launch_bounds__(128) bn_bwd_kernel(const float* __restrict__ dz1, const float* __restrict__ xh,
-                                                     int batch, int dim, const uint8_t* __restrict__ keep,
-                                                     float keep_scale, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta) {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= dim) return;
+// dgamma[d] = sum_b dz1 keep1 xh, dbeta[d] = sum_b dz1 keep1 — rows dealt over the block's warps like colsum_kernel
+__global__ void __launch_bounds__(32 * RED_WARPS) bn_bwd_kernel(const float* __restrict__ dz1, const float* __restrict__ xh,
+                                                                int batch, int dim, const uint8_t* __restrict__ keep,
+                                                                float keep_scale, float* __restrict__ dgamma,
+                                                                float* __restrict__ dbeta) {
+    __shared__ float pg[RED_WARPS][32];
+    __shared__ float pb[RED_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = blockIdx.x * 32 + lane;
     float sg = 0.f, sb = 0.f;
-    for (int b = 0; b < batch; ++b) {
-        const size_t i = static_cast<size_t>(b) * dim + d;
-        float dy = dz1[i];
-        if (keep != nullptr) dy = keep[i] ? dy * keep_scale : 0.f;
-        sg += dy * xh[i];
-        sb += dy;
+    if (d < dim)
+        for (int b = warp; b < batch; b += RED_WARPS) {
+            const size_t i = static_cast<size_t>(b) * dim + d;
+            float dy = dz1[i];
+            if (keep != nullptr) dy = keep[i] ? dy * keep_scale : 0.f;
+            sg += dy * xh[i];
+            sb += dy;
+        }
+    pg[warp][lane] = sg;
+    pb[warp][lane] = sb;
+    __syncthreads();
+    if (warp == 0 && d < dim) {
+        float tg = 0.f, tb = 0.f;
+#pragma unroll
+        for (int w = 0; w < RED_WARPS; ++w) {
+            tg += pg[w][lane];
+            tb += pb[w][lane];
+        }
+        dgamma[d] = tg;
+        dbeta[d] = tb;
     }
-    dgamma[d] = sg;
-    dbeta[d] = sb;
 }
 
 // torch.optim.AdamW with grad = grad_scale * bucket[i] / bucket[wsum_index]; a head with no labelled row in the global
@@ -214,6 +267,32 @@ __global__ void __launch_bounds__(256) adamw_ex_kernel(float* __restrict__ p, fl
     const float wsum = bucket[wsum_index];
     if (!(wsum > 0.f)) return;
     const float inv = grad_scale / wsum;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < numel;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float g = bucket[i] * inv;
+        float pi = p[i] * (1.f - lr * wd);
+        const float mi = beta1 * m[i] + (1.f - beta1) * g;
+        const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+        m[i] = mi;
+        v[i] = vi;
+        pi -= (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+        p[i] = pi;
+    }
+}
+
+// the same update with everything that changes between optimisation steps read from device memory — the step number
+// (steps completed so far; this is step *steps_done + 1) and the task weight — so a multitask step replays from a CUDA graph
+__global__ void __launch_bounds__(256) adamw_ex_dev_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                           const float* __restrict__ bucket, int64_t numel,
+                                                           int64_t wsum_index, const float* __restrict__ grad_scale,
+                                                           const int64_t* __restrict__ steps_done, float lr, float beta1,
+                                                           float beta2, float eps, float wd) {
+    const float wsum = bucket[wsum_index];
+    if (!(wsum > 0.f)) return;
+    const float step = static_cast<float>(*steps_done + 1);
+    const float bc1 = 1.f - powf(beta1, step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
+    const float inv = *grad_scale / wsum;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < numel;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const float g = bucket[i] * inv;
@@ -290,20 +369,16 @@ extern "C" int vlmfw_probe_deep_grads(const float* x, const int64_t* targets, in
     VLMFW_LAUNCH_CHECK();
     // backward
     if ((rc = sgemm<true, false>(dlog, classes, z2, hidden, dW2, hidden, classes, hidden, batch, s)) != VLMFW_OK) return rc;
-    colsum_kernel<<<1, 128, 0, s>>>(dlog, batch, classes, classes, db2);
-    VLMFW_LAUNCH_CHECK();
-    colsum_kernel<<<1, 128, 0, s>>>(loss_b, batch, 1, 1, tail);
-    VLMFW_LAUNCH_CHECK();
-    colsum_kernel<<<1, 128, 0, s>>>(w_b, batch, 1, 1, tail + 1);
+    ce_sums_kernel<<<(classes + 2 + 31) / 32, 32 * RED_WARPS, 0, s>>>(dlog, loss_b, w_b, batch, classes, db2, tail);
     VLMFW_LAUNCH_CHECK();
     if ((rc = sgemm<false, false>(dlog, classes, W2, hidden, dz2, hidden, batch, hidden, classes, s)) != VLMFW_OK) return rc;
     gelu_bwd_kernel<<<eb, 256, 0, s>>>(dz2, a, batch, hidden, keep2, ks);
     VLMFW_LAUNCH_CHECK();
     if ((rc = sgemm<true, false>(dz2, hidden, z1, dim, dW1, dim, hidden, dim, batch, s)) != VLMFW_OK) return rc;
-    colsum_kernel<<<(hidden + 127) / 128, 128, 0, s>>>(dz2, batch, hidden, hidden, db1);
+    colsum_kernel<<<(hidden + 31) / 32, 32 * RED_WARPS, 0, s>>>(dz2, batch, hidden, hidden, db1);
     VLMFW_LAUNCH_CHECK();
     if ((rc = sgemm<false, false>(dz2, hidden, W1, dim, dz1, dim, batch, dim, hidden, s)) != VLMFW_OK) return rc;
-    bn_bwd_kernel<<<(dim + 127) / 128, 128, 0, s>>>(dz1, xh, batch, dim, keep1, ks, dgamma, dbeta);
+    bn_bwd_kernel<<<(dim + 31) / 32, 32 * RED_WARPS, 0, s>>>(dz1, xh, batch, dim, keep1, ks, dgamma, dbeta);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }
@@ -321,6 +396,22 @@ extern "C" int vlmfw_probe_adamw_ex(float* params, float* exp_avg, float* exp_av
     adamw_ex_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, exp_avg, exp_avg_sq, bucket, numel,
                                                                          weight_sum_index, grad_scale, lr, beta1, beta2,
                                                                          eps, weight_decay, bc1, bc2_sqrt);
+    VLMFW_LAUNCH_CHECK();
+    return VLMFW_OK;
+}
+
+extern "C" int vlmfw_probe_adamw_ex_dev(float* params, float* exp_avg, float* exp_avg_sq, const float* bucket, int64_t numel,
+                                        int64_t weight_sum_index, const float* grad_scale, const int64_t* steps_done, float lr,
+                                        float beta1, float beta2, float eps, float weight_decay, void* stream) {
+    VLMFW_REQUIRE(params && exp_avg && exp_avg_sq && bucket && grad_scale && steps_done && numel > 0,
+                  "probe_adamw_ex_dev: bad arguments");
+    int rc = device_check();
+    if (rc != VLMFW_OK) return rc;
+    int grid = static_cast<int>((numel + 255) / 256);
+    if (grid > 1184) grid = 1184;
+    adamw_ex_dev_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, exp_avg, exp_avg_sq, bucket, numel,
+                                                                             weight_sum_index, grad_scale, steps_done, lr,
+                                                                             beta1, beta2, eps, weight_decay);
     VLMFW_LAUNCH_CHECK();
     return VLMFW_OK;
 }

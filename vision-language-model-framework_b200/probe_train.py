@@ -95,9 +95,10 @@ class ProbeTrainStep:
 
     def exchange_description(self) -> str:
         if self._comm_h is not None:
-            return ("fused into the step's kernels over NVLink peer memory: bn_stats / backward store their sums into every "
-                    "rank's slots and raise flags, the mask / AdamW kernels wait on local flags and add the slots in rank order "
-                    "(BatchNorm sums [2D] fp64, gradient bucket [C*D + C + 2D + 2] fp32); no collective kernel")
+            return ("fused into the step's kernels over NVLink peer memory: bn_stats / backward store every sum together with the "
+                    "exchange's flag (one 8- / 16-byte store) into every rank's slots, the mask / AdamW kernels poll their local "
+                    "slots and add them in rank order (BatchNorm sums [2D] fp64, gradient bucket [C*D + C + 2D + 2] fp32); no "
+                    "fence, no collective kernel")
         return ("2 dependent NCCL all-reduces per step: BatchNorm batch sums [2D] fp64, then the flat gradient bucket "
                 "[C*D + C + 2D + 2] fp32")
 
@@ -477,6 +478,7 @@ class MultiTaskProbeTrainStep:
         self._offsets = [sum(sizes[:i]) for i in range(len(sizes))]
         self.step_count = 0
         self.last_logits: Dict[str, torch.Tensor] = {}
+        self._graph = None  # set by capture()
 
     # ---- task weights (multitask_trainer.py:209-226, 235-263) ---------------------------------------------------
     def on_epoch_start(self) -> Dict[str, float]:
@@ -573,6 +575,131 @@ class MultiTaskProbeTrainStep:
         idx = torch.tensor([o + h.n_params + k for o, h in zip(self._offsets, self.heads.values()) for k in (0, 1)],
                            device=self.device)
         tails = self.bucket[idx].tolist()
+        losses = {t: (tails[2 * i] / tails[2 * i + 1] if tails[2 * i + 1] > 0 else None) for i, t in enumerate(self.tasks)}
+        if self.use_running_means:
+            self._update_ema(losses)
+        return losses
+
+    # ---- the whole step as ONE CUDA graph -----------------------------------------------------------------------
+    # launches of this library per graph-form step: bn_stats, then per head 2 (linear: 1) mask draws + the gradient kernels
+    # (deeper: 13, linear: 2), then per head AdamW + BatchNorm running statistics, the step counter
+    def kernels_per_step(self) -> int:
+        per_head = (2 + 13 if self.hidden else 1 + 2) if self.dropout_p > 0 else (13 if self.hidden else 2)
+        return 1 + len(self.tasks) * (per_head + 2) + 1
+
+    def capture(self, b_local: int, n_global: Optional[int] = None, global_offset: int = 0) -> None:
+        """Capture one optimisation step (all heads) for a fixed local batch size into a CUDA graph, like
+        ``ProbeTrainStep.capture``: the dropout keys and AdamW's bias corrections come from a device-side step counter
+        (``vlmfw_dropout_keep_mask_dev``, ``vlmfw_probe_adamw_ex_dev``), the task weights from a device vector that
+        ``on_epoch_start`` refreshes, the per-head [loss_sum, weight_sum] pairs land in pinned memory by a copy node. A
+        5-head deeper step is ~80 launches eagerly; replayed it is one."""
+        import torch.distributed as dist
+
+        dev, d, lib = self.device, self.dim, self._lib
+        n_global = b_local if n_global is None else n_global
+        t_count = len(self.tasks)
+        self._g_shape = (b_local, n_global, global_offset)
+        self._g_x = torch.zeros(b_local, d, device=dev)
+        self._g_y = torch.full((t_count, b_local), -1, dtype=torch.int64, device=dev)  # task-major, like phase2's y.t()
+        self._g_steps_done = torch.tensor([self.step_count], dtype=torch.int64, device=dev)
+        self._g_steps_done_value = self.step_count
+        self._g_tw_value = [float(self.current_task_weights[t]) for t in self.tasks]
+        self._g_tw = torch.tensor(self._g_tw_value, dtype=torch.float32, device=dev)
+        self._g_tails_idx = torch.tensor([o + h.n_params + k for o, h in zip(self._offsets, self.heads.values())
+                                          for k in (0, 1)], device=dev)
+        self._g_tails_dev = torch.zeros(2 * t_count, device=dev)
+        self._g_tails = torch.zeros(2 * t_count, dtype=torch.float32).pin_memory()
+        bufs = []
+        for h in self.heads.values():
+            n = int(lib.vlmfw_probe_deep_scratch_floats(b_local, d, self.hidden, h.classes)) if self.hidden \
+                else b_local * (h.classes + 2)
+            bufs.append({
+                "logits": torch.empty(b_local, h.classes, device=dev), "scratch": torch.empty(n, device=dev),
+                "k1": torch.empty(b_local, d, dtype=torch.uint8, device=dev) if self.dropout_p > 0 else None,
+                "k2": torch.empty(b_local, self.hidden, dtype=torch.uint8, device=dev)
+                if (self.dropout_p > 0 and self.hidden) else None})
+        self._g_bufs = bufs
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if distributed:  # communicator set-up cannot be captured
+            allreduce_sum_(torch.zeros(2, dtype=torch.float64, device=dev), self.group)
+            allreduce_sum_(torch.zeros(2, device=dev), self.group)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(dev), torch.cuda.graph(graph):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.vlmfw_probe_bn_stats(self._g_x.data_ptr(), b_local, d, self.stats.data_ptr(), st))
+            allreduce_sum_(self.stats, self.group)
+            for i, (t, h) in enumerate(self.heads.items()):
+                bf = bufs[i]
+                bucket = self.bucket[self._offsets[i]: self._offsets[i] + h.n_params + 2]
+                cw = self.class_weights[t]
+                key0 = mask_key(self.seed, 0, i)
+                if bf["k1"] is not None:
+                    _lib.check(lib.vlmfw_dropout_keep_mask_dev(bf["k1"].data_ptr(), b_local, d, global_offset, key0,
+                                                               self._g_steps_done.data_ptr(), MASK_KEY_STEP_STRIDE,
+                                                               float(self.dropout_p), st))
+                if bf["k2"] is not None:
+                    _lib.check(lib.vlmfw_dropout_keep_mask_dev(bf["k2"].data_ptr(), b_local, self.hidden, global_offset,
+                                                               (key0 + 1) & 0xFFFFFFFFFFFFFFFF,
+                                                               self._g_steps_done.data_ptr(), MASK_KEY_STEP_STRIDE,
+                                                               float(self.dropout_p), st))
+                k1 = None if bf["k1"] is None else bf["k1"].data_ptr()
+                k2 = None if bf["k2"] is None else bf["k2"].data_ptr()
+                if self.hidden:
+                    _lib.check(lib.vlmfw_probe_deep_grads(
+                        self._g_x.data_ptr(), self._g_y[i].data_ptr(), b_local, d, self.hidden, h.classes,
+                        self.stats.data_ptr(), n_global, self.bn_eps, h.params.data_ptr(),
+                        None if cw is None else cw.data_ptr(), k1, k2, self.dropout_p, bucket.data_ptr(),
+                        bf["logits"].data_ptr(), bf["scratch"].data_ptr(), st))
+                else:
+                    _lib.check(lib.vlmfw_probe_linear_grads(
+                        self._g_x.data_ptr(), self._g_y[i].data_ptr(), b_local, d, h.classes, self.stats.data_ptr(), n_global,
+                        self.bn_eps, h.view("0.weight").data_ptr(), h.view("0.bias").data_ptr(),
+                        h.view("2.weight").data_ptr(), h.view("2.bias").data_ptr(), None if cw is None else cw.data_ptr(),
+                        k1, self.dropout_p, bucket.data_ptr(), bf["logits"].data_ptr(), bf["scratch"].data_ptr(), st))
+            allreduce_sum_(self.bucket, self.group)
+            for i, (t, h) in enumerate(self.heads.items()):
+                bucket = self.bucket[self._offsets[i]: self._offsets[i] + h.n_params + 2]
+                _lib.check(lib.vlmfw_probe_adamw_ex_dev(
+                    h.params.data_ptr(), h.exp_avg.data_ptr(), h.exp_avg_sq.data_ptr(), bucket.data_ptr(), h.n_params,
+                    h.n_params + 1, self._g_tw.data_ptr() + 4 * i, self._g_steps_done.data_ptr(), self.lr, self.betas[0],
+                    self.betas[1], self.eps, self.wd, st))
+                _lib.check(lib.vlmfw_probe_bn_running_update(
+                    h.running_mean.data_ptr(), h.running_var.data_ptr(), self.stats.data_ptr(), d, n_global,
+                    self.bn_momentum, st))
+            _lib.check(lib.vlmfw_counter_add(self._g_steps_done.data_ptr(), 1, st))
+            torch.index_select(self.bucket, 0, self._g_tails_idx, out=self._g_tails_dev)
+            self._g_tails.copy_(self._g_tails_dev, non_blocking=True)
+        self._graph = graph
+
+    def release_graph(self) -> None:
+        """Drop the captured graph (call before ``torch.distributed.destroy_process_group()``)."""
+        self._graph = None
+
+    def step_graph(self, x: torch.Tensor, y: torch.Tensor) -> Dict[str, Optional[float]]:
+        """``step`` through the captured graph: ``x [B_local, D]``, ``y [B_local, T]`` (host or device), shapes as captured."""
+        if self._graph is None:
+            raise RuntimeError("step_graph before capture()")
+        if y.dim() == 1:
+            y = y[:, None]
+        if tuple(x.shape) != (self._g_shape[0], self.dim) or tuple(y.shape) != (self._g_shape[0], len(self.tasks)):
+            raise ValueError(f"step_graph: batch {tuple(x.shape)} / {tuple(y.shape)} does not match the captured shape")
+        if self._g_steps_done_value != self.step_count:  # eager steps ran in between
+            self._g_steps_done.fill_(self.step_count)
+        tw = [float(self.current_task_weights[t]) for t in self.tasks]
+        if tw != self._g_tw_value:
+            self._g_tw.copy_(torch.tensor(tw, dtype=torch.float32))
+            self._g_tw_value = tw
+        self._g_x.copy_(x, non_blocking=True)
+        self._g_y.copy_(y.t(), non_blocking=True)
+        self._graph.replay()
+        self.last_logits = {t: self._g_bufs[i]["logits"] for i, t in enumerate(self.tasks)}
+        self.step_count += 1
+        self._g_steps_done_value = self.step_count
+        for h in self.heads.values():
+            h.num_batches_tracked += 1
+        torch.cuda.current_stream(self.device).synchronize()
+        tails = self._g_tails.tolist()
         losses = {t: (tails[2 * i] / tails[2 * i + 1] if tails[2 * i + 1] > 0 else None) for i, t in enumerate(self.tasks)}
         if self.use_running_means:
             self._update_ema(losses)
