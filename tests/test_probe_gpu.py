@@ -42,7 +42,7 @@ def test_argmax_first_max_tie_rule(cuda_device):
     assert amax[:, 0].tolist() == [1] * 5 == torch.tensor([1.0, 3.0, 3.0, 2.0]).argmax().repeat(5).tolist()
 
 
-@pytest.mark.parametrize("dim,classes,n,p", [(1152, 9, 256, 0.3), (144, 5, 33, 0.0), (1024, 2, 64, 0.5)])
+@pytest.mark.parametrize("dim,classes,n,p", [(1152, 9, 256, 0.3), (144, 5, 33, 0.0), (1024, 2, 64, 0.5), (256, 9, 2048, 0.3)])
 def test_train_steps_match_reference_adamw(cuda_device, dim, classes, n, p):
     g = torch.Generator().manual_seed(n)
     state = O.seeded_head_params(dim, classes, 0, seed=9)

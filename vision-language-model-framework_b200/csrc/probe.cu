@@ -132,42 +132,75 @@ __device__ __forceinline__ void dp_put_f64(const DpLink& lk, size_t at, int len,
                      : "memory");
     }
 }
-// sum over ranks (rank order) of element `at` of this rank's bucket / stats slots, each polled until it carries `flag`
+// sum over ranks (rank order) of element `at` of this rank's bucket / stats slots, each polled until it carries `flag`.
+// The loads of all ranks' slots are issued together and only the missing ones are polled again: one L2 round trip when
+// everything has arrived, instead of `world` dependent ones (8 ranks: ~4 us per consumer kernel with a slot-by-slot loop).
 __device__ __forceinline__ float dp_get_f32(const DpLink& lk, size_t at, int nb, uint32_t flag) {
-    float t = 0.f;
-    for (int r = 0; r < lk.world; ++r) {
-        const uint2* src = lk.bucket[lk.rank] + static_cast<size_t>(r) * nb + at;
-        uint32_t x, f;
-        long long spins = 0;
-        do {
-            asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(f) : "l"(src) : "memory");
-            if (f != flag && ++spins > DP_SPIN_LIMIT) {
-                *lk.error = 1;
-                break;
+    float vals[DP_MAX_WORLD];
+    unsigned pending = (1u << lk.world) - 1u;
+    long long spins = 0;
+    const uint2* base = lk.bucket[lk.rank] + at;
+    while (pending) {
+        uint32_t x[DP_MAX_WORLD], f[DP_MAX_WORLD];
+#pragma unroll
+        for (int r = 0; r < DP_MAX_WORLD; ++r)
+            if (pending >> r & 1u)
+                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];"
+                             : "=r"(x[r]), "=r"(f[r])
+                             : "l"(base + static_cast<size_t>(r) * nb)
+                             : "memory");
+#pragma unroll
+        for (int r = 0; r < DP_MAX_WORLD; ++r)
+            if ((pending >> r & 1u) && f[r] == flag) {
+                vals[r] = __uint_as_float(x[r]);
+                pending &= ~(1u << r);
             }
-        } while (f != flag);
-        t += __uint_as_float(x);
+        if (pending && ++spins > DP_SPIN_LIMIT) {
+            *lk.error = 1;
+#pragma unroll
+            for (int r = 0; r < DP_MAX_WORLD; ++r)
+                if (pending >> r & 1u) vals[r] = 0.f;
+            break;
+        }
     }
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < DP_MAX_WORLD; ++r)
+        if (r < lk.world) t += vals[r];
     return t;
 }
 __device__ __forceinline__ double dp_get_f64(const DpLink& lk, size_t at, int len, uint32_t flag) {
-    double t = 0.0;
-    for (int r = 0; r < lk.world; ++r) {
-        const uint4* src = lk.stats[lk.rank] + static_cast<size_t>(r) * len + at;
-        uint32_t lo, f0, hi, f1;
-        long long spins = 0;
-        do {
-            asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1)
-                         : "l"(src)
-                         : "memory");
-            if ((f0 != flag || f1 != flag) && ++spins > DP_SPIN_LIMIT) {
-                *lk.error = 1;
-                break;
+    double vals[DP_MAX_WORLD];
+    unsigned pending = (1u << lk.world) - 1u;
+    long long spins = 0;
+    const uint4* base = lk.stats[lk.rank] + at;
+    while (pending) {
+        uint32_t lo[DP_MAX_WORLD], f0[DP_MAX_WORLD], hi[DP_MAX_WORLD], f1[DP_MAX_WORLD];
+#pragma unroll
+        for (int r = 0; r < DP_MAX_WORLD; ++r)
+            if (pending >> r & 1u)
+                asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(lo[r]), "=r"(f0[r]), "=r"(hi[r]), "=r"(f1[r])
+                             : "l"(base + static_cast<size_t>(r) * len)
+                             : "memory");
+#pragma unroll
+        for (int r = 0; r < DP_MAX_WORLD; ++r)
+            if ((pending >> r & 1u) && f0[r] == flag && f1[r] == flag) {
+                vals[r] = __longlong_as_double(static_cast<long long>((static_cast<uint64_t>(hi[r]) << 32) | lo[r]));
+                pending &= ~(1u << r);
             }
-        } while (f0 != flag || f1 != flag);
-        t += __longlong_as_double(static_cast<long long>((static_cast<uint64_t>(hi) << 32) | lo));
+        if (pending && ++spins > DP_SPIN_LIMIT) {
+            *lk.error = 1;
+#pragma unroll
+            for (int r = 0; r < DP_MAX_WORLD; ++r)
+                if (pending >> r & 1u) vals[r] = 0.0;
+            break;
+        }
     }
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < DP_MAX_WORLD; ++r)
+        if (r < lk.world) t += vals[r];
     return t;
 }
 
@@ -535,8 +568,11 @@ extern "C" int vlmfw_probe_linear_grads(const float* x, const int64_t* targets, 
     VLMFW_REQUIRE(batch > 0 && dim > 0 && classes > 0 && classes <= MAX_CLASSES && n_global >= batch,
                   "probe_linear_grads: bad shape");
     VLMFW_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "probe_linear_grads: dropout_p out of range");
-    VLMFW_REQUIRE(static_cast<size_t>(batch) * classes * sizeof(float) <= 48 * 1024,
-                  "probe_linear_grads: batch*classes too large for one launch (split the batch)");
+    // the backward kernel stages dlogits [B*C] plus its per-warp partials in shared memory (opt-in 96 KB): B*C <= ~21 k
+    VLMFW_REQUIRE((((static_cast<size_t>(batch) * classes + 31) & ~static_cast<size_t>(31)) +
+                   static_cast<size_t>(BWD_WARPS) * (classes + 2) * 32) * sizeof(float) <= 96 * 1024,
+                  "probe_linear_grads: batch*classes = %d*%d exceeds the backward kernel's 96 KB staging (split the batch)", batch,
+                  classes);
     int rc = device_check();
     if (rc != VLMFW_OK) return rc;
     TrainArgs a;
@@ -797,7 +833,9 @@ extern "C" int vlmfw_probe_linear_step_dp(const vlmfw_probe_step* a, vlmfw_comm*
     VLMFW_REQUIRE(B > 0 && D > 0 && C > 0 && C <= MAX_CLASSES && a->n_global >= B, "probe_linear_step_dp: bad shape");
     VLMFW_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "probe_linear_step_dp: dropout_p out of range");
     VLMFW_REQUIRE(a->dropout_p == 0.f || a->keep != nullptr, "probe_linear_step_dp: dropout needs a keep-mask buffer");
-    VLMFW_REQUIRE(static_cast<size_t>(B) * C * sizeof(float) <= 48 * 1024, "probe_linear_step_dp: batch*classes too large for one launch");
+    VLMFW_REQUIRE((((static_cast<size_t>(B) * C + 31) & ~static_cast<size_t>(31)) + static_cast<size_t>(BWD_WARPS) * (C + 2) * 32) *
+                          sizeof(float) <= 96 * 1024,
+                  "probe_linear_step_dp: batch*classes exceeds the backward kernel's 96 KB staging (split the batch)");
     const int64_t n_params = static_cast<int64_t>(C) * D + C + 2 * D;
     VLMFW_REQUIRE(c->stats_len == 2 * D && c->bucket_len == n_params + 2, "probe_linear_step_dp: the communicator was created for other sizes");
     int rc = device_check();

@@ -306,22 +306,35 @@ def ensure_features(model, img_dataset, split: str, features_dir, task: str, bat
     from .parallel import shard_range
 
     fpath = Path(features_dir) / f"{split}_features.pt"
-    if not fpath.exists():
-        rank, world = _world(group)
+    rank, world = _world(group)
+    have = fpath.exists()
+    if world > 1:
+        # ONE decision for the whole group (rank 0's view of the file system): ranks that disagree — a stale or partially
+        # visible cache file — would otherwise split between loading and the writer's barriers and hang each other
+        flag = [have]
+        dist.broadcast_object_list(flag, src=0, group=group)
+        have = bool(flag[0])
+    if not have:
         lo, hi = shard_range(len(img_dataset), rank, world)
-        loader = DataLoader(Subset(img_dataset, range(lo, hi)), batch_size=batch_size, shuffle=False,
-                            num_workers=num_workers, drop_last=False, collate_fn=lambda b: ([s[0] for s in b], [s[1] for s in b]))
         was_training = model.training
         model.eval()
         writer = None
-        with torch.no_grad():
-            for images_list, targets_list in loader:
-                feats = model.extract_features(images_list)
-                if writer is None:
-                    writer = FeatureCacheWriter(feats.shape[1], feats.device, group=group)
-                writer.add(feats.float(), targets_to_matrix(targets_list, [task])[:, 0])
+        if hi > lo:
+            loader = DataLoader(Subset(img_dataset, range(lo, hi)), batch_size=batch_size, shuffle=False, num_workers=num_workers,
+                                drop_last=False, collate_fn=lambda b: ([s[0] for s in b], [s[1] for s in b]))
+            with torch.no_grad():
+                for images_list, targets_list in loader:
+                    feats = model.extract_features(images_list)
+                    if writer is None:
+                        writer = FeatureCacheWriter(feats.shape[1], feats.device, group=group)
+                    writer.add(feats.float(), targets_to_matrix(targets_list, [task])[:, 0])
         if writer is None:
-            raise ValueError("empty dataset shard: fewer samples than ranks")
+            if world == 1:
+                raise ValueError("empty dataset: nothing to cache")
+            # fewer samples than ranks: this rank contributes an empty shard (and still meets the writer's barriers)
+            bb = model.backbone
+            dev = bb._tower_device() if hasattr(bb, "_tower_device") else next(model.parameters()).device
+            writer = FeatureCacheWriter(int(bb.output_dim), dev, group=group)
         writer.finalize(fpath)
         if was_training:
             model.train()
