@@ -1,4 +1,9 @@
 set -x
-PT="python -m pytest -x -q -m gpu --timeout 180 --timeout-method thread"
-timeout 300 $PT tests/test_probe_gpu.py tests/test_probe_multitask.py tests/test_sinks.py > gpurun_out/r2i_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r2i_tests.log
-bash tools/run_ncu_towers.sh r2i
+for st in 0 601 1201 1801; do
+echo "== stagger $st"; VLMFW_WB_STAGGER=$st timeout 120 python tools/bench_kernels.py --only att --no-cublas 2>&1 | grep kernel
+done
+python - <<'PY'
+# which CTAs share an SM? launch a tiny probe: 296 CTAs x 384 threads with 100 KB smem, record smid
+import torch
+from torch.utils.cpp_extension import load_inline
+PY

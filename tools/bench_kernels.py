@@ -62,7 +62,9 @@ def main():
             fn = lambda: ops.gemm_tn(a, w, bias, resid=h, out=h, block_n=args.block_n)  # noqa: E731
         else:
             out = pad(m, n)
-            act = specs.ACT_GELU_TANH if kind == "gelu" else specs.ACT_NONE
+            # each tower's own activation: SigLIP gelu_pytorch_tanh, CLIP quick_gelu, EVA gelu (erf)
+            gelu = specs.ACT_QUICK_GELU if name.startswith("clip") else specs.ACT_GELU_ERF if name.startswith("eva") else specs.ACT_GELU_TANH
+            act = gelu if kind == "gelu" else specs.ACT_NONE
             fn = lambda: ops.gemm_tn(a, w, bias, act=act, out=out, block_n=args.block_n)  # noqa: E731
         med, best = timeit(fn)
         wt = w.t()

@@ -2,25 +2,37 @@
 // Restates hf integrations/sdpa_attention.py:92 as called from modeling_siglip.py:285-309, modeling_clip.py:310-334 and
 // modeling_blip_2.py:328-351 — same contract and layouts as attention_tc.cu (qkv [B*S, 3D] in, ctx [B*S, D] out).
 //
-// What the round-1 kernel (attention_tc.cu, 64-key blocks, P through shared memory) measured: 188 us per SigLIP layer at
-// B = 256, tensor pipe 23.7 % active, 2.8x above the exponential (MUFU) floor — every 64-key block paid a fixed chain of
-// TMEM load, P tile to shared memory + proxy fence, three mbarrier round trips and eight small P.V MMAs issued by one
-// thread at ~75 cycles each. This kernel removes those per-block costs:
-//   * keys in blocks of 128: ONE score MMA 128 x 128 x dh per block (half the barrier round trips per key);
-//   * the probabilities never touch shared memory: each softmax thread holds its row's 128 scores in registers, writes P
-//     back as packed 16-bit pairs into the TMEM columns its scores came from (tcgen05.st) and P.V reads its A operand from
-//     TMEM (tcgen05.mma with A in tensor memory) — no st.shared, no fence.proxy.async, no P tiles (64 KB per CTA freed);
-//   * P.V is issued per 64-key chunk as soon as that chunk's P is in TMEM, by TWO single-thread issuers for the head
-//     dims with a tail tile (72 = 64 + 8 -> 16, 88 = 64 + 24 -> 32): the main-tile and tail-tile MMAs write disjoint TMEM
-//     columns, so they need no order between them and the issue cost per key halves;
-//   * the lone last key of the class-token towers (CLIP 577 = 4.5 x 128 + 1, EVA 257 = 2 x 128 + 1) is folded in on CUDA
-//     cores by the softmax threads (one dot product and one axpy per query row) instead of costing a whole block step.
-// Still: persistent, TWO CTAs per SM (256 TMEM columns each: S / P [0,128), O [128, 128 + dh_padded)), one thread = one
-// query row = one TMEM lane, fp32 softmax with exp2 and a lazily raised running max, O / l -> 16-bit -> shared-memory
-// staging -> TMA store into ctx[b, tok, h, :].
+// What the round-1 kernel (attention_tc.cu, P through shared memory) measured: 188 us per SigLIP layer at B = 256, tensor
+// pipe 23.7 % active — every 64-key block paid a fixed chain of TMEM load, P tile to shared memory + proxy fence, three
+// mbarrier round trips and eight small P.V MMAs issued by one thread at ~75 cycles each. This kernel:
+//   * keeps the probabilities out of shared memory: each softmax thread holds its row's 64 scores of a key block in
+//     registers, writes P as packed 16-bit pairs into tensor memory (tcgen05.st) and P.V takes its A operand from there
+//     (tcgen05.mma with A in TMEM) — no st.shared, no fence.proxy.async, no P tiles (64 KB per CTA freed);
+//   * gives P its own two TMEM buffers, so the ONE score buffer goes back to the score issuer as soon as the softmax warps
+//     hold the block in registers: the score MMA of block t + 1 runs under the exponentials of block t, and the softmax
+//     warps request block t + 1 from TMEM right after handing P of block t to the store (software pipeline across items);
+//   * issues P.V per 64-key block by TWO single-thread issuers for the head dims with a tail tile (72 = 64 + 8 -> 16,
+//     88 = 64 + 24 -> 32): main-tile and tail-tile MMAs write disjoint TMEM columns, so they need no order between them;
+//   * folds the lone last key of the class-token towers (CLIP 577 = 9 x 64 + 1, EVA 257 = 4 x 64 + 1) in on CUDA cores
+//     (one dot product by the epilogue warpgroup, one exponential and one axpy per query row) instead of a block step;
+//   * feeds everything from ONE loader thread that blocks in order on Q, K(t), V(t - 1) — two hardware-sleep waits and
+//     four TMA issues per block. The first loader polled three streams with test_wait and rebuilt coordinates by
+//     division: 2250 cycles per block, as long as the softmax chain itself (found with the exponentials compiled out:
+//     the kernel got only 8 % faster and the score issuer then waited for K).
+// Persistent, TWO CTAs per SM (256 TMEM columns each: S [0,64), P0 / P1 [64,128), O [128, 128 + dh_padded)), one thread
+// = one query row = one TMEM lane, fp32 softmax with exp2 and a lazily raised running max, O / l -> 16-bit -> shared-
+// memory staging -> TMA store into ctx[b, tok, h, :].
 //
-// Roles (256 threads): warp 0 TMA loader (Q tile; K and V rings), warp 1 score issuer, warp 2 P.V issuer (main tile),
-// warp 3 P.V issuer (tail tile; idle for head_dim 64), warps 4..7 softmax + epilogue.
+// Roles (384 threads): warpgroup 0 = TMA loader, score issuer, P.V issuer (main tile), P.V issuer (tail tile; idle for
+// head_dim 64); warpgroup 1 = softmax; warpgroup 2 = lone-key scores + epilogue.
+//
+// Where the time goes now (clock64 timeline of one CTA, SigLIP, 2550 cycles per 64-key block and CTA): reading the 32 KB
+// score block out of tensor memory ~430, max + 64 exponentials + pack ~1150 (917 with the SM to itself: the MUFU pipe
+// takes 8 cycles per warp instruction), P store + hand-offs ~600, barrier waits ~350. Compiling the exponentials AND the
+// 16-bit pack out leaves 2390: the block period is the serial chain of one warp per row quarter — TMEM load, arithmetic,
+// TMEM store, three mbarrier hand-offs — of which two CTAs per SM overlap at most two. Tried on top and dropped (no
+// change): K and V of a block through one TMA (a box two deep along q|k|v), a half-period start offset between the two
+// CTAs of an SM, polynomial exp2 on the FMA pipe for part of the elements.
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -76,11 +88,15 @@ struct WbParams {
     float scale_log2;
 };
 
-// TMEM columns (256 allocated per CTA): two score buffers S0 [0,64), S1 [64,128) (fp32 scores of a 64-key block; block t
-// uses buffer t & 1), each overwritten in place by its P (packed 16-bit pairs in the buffer's first 32 columns);
-// O [128, 128 + DHP)
+// TMEM columns (256 allocated per CTA): ONE score buffer S [0,64) (fp32 scores of the current 64-key block), two
+// probability buffers P0 [64,96), P1 [96,128) (packed 16-bit pairs; block t uses buffer t & 1), O [128, 128 + DHP).
+// S belongs to the score issuer again as soon as the softmax warps hold the block in registers (s_free), so the score MMA
+// of block t + 1 runs under the exponentials of block t instead of behind the P.V MMAs of block t - 1 (the first layout
+// of this kernel kept P in the columns its scores came from: two S buffers, each held until its P.V had retired, and the
+// softmax warps could not fetch block t + 1 before they had finished block t).
+constexpr uint32_t TM_S = 0;
 constexpr uint32_t TM_O = 128;
-__device__ __forceinline__ constexpr uint32_t tm_s(int buf) { return static_cast<uint32_t>(buf) * KBW; }
+__device__ __forceinline__ constexpr uint32_t tm_p(int buf) { return 64u + static_cast<uint32_t>(buf) * (KBW / 2); }
 
 // D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 columns of packed 16-bit pairs per K-step of 16
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -192,8 +208,9 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     uint64_t* bars = reinterpret_cast<uint64_t*>(sLone + C::LONE_BYTES);
     uint64_t* q_full = bars + 0;    // [2]
     uint64_t* q_empty = bars + 2;   // [2] last score MMA of the item retired AND the four softmax warps are done with the slot
-    uint64_t* s_full = bars + 4;    // [2] score buffer written by the score MMA
-    uint64_t* s_empty = bars + 6;   // [2] all P.V MMAs of the block retired: the buffer's S / P columns may be overwritten
+    uint64_t* s_full = bars + 4;    // score buffer written by the score MMA (completion t = block t)
+    uint64_t* s_free = bars + 5;    // the four softmax warps have block t's scores in registers
+    uint64_t* p_empty = bars + 6;   // [2] all P.V MMAs of the block retired: its P buffer may be overwritten
     uint64_t* p_full = bars + 8;    // [2] P of the block written to TMEM by the four softmax warps
     uint64_t* o_full = bars + 10;
     uint64_t* o_empty = bars + 11;
@@ -220,9 +237,10 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         mbar_init(o_full, C::NPV);
         mbar_init(o_empty, 4);
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 4);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1);
-            mbar_init(&s_empty[i], C::NPV);
+            mbar_init(&p_empty[i], C::NPV);
             mbar_init(&p_full[i], 4);
             mbar_init(&q_full[i], 1);
             mbar_init(&q_empty[i], 1 + 4);
@@ -273,61 +291,51 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             const uint8_t* qkv8 = static_cast<const uint8_t*>(p.qkv);
             const size_t row_bytes = static_cast<size_t>(3) * p.D * 2;
             WTR_DECL;
-            // Three independent request streams — Q tiles (slot = item & 1, one item ahead: the Q load's ~2000 cycles sat on
-            // every item's critical path when the tile was single-buffered), K tiles and V tiles (one of each per 64-key
-            // block) — served by ONE thread that never blocks on a single stream: an in-order loader parked on a V slot
-            // (freed by P.V progress) held back the next K tile, and the score issuer then waited for K half of the time.
-            const int T = n_local * J;          // key blocks of this CTA
-            int tq = 0, tk = 0, uv = 0;         // next Q item / K block / V block to request
-            auto coords_of_block = [&](int t, int& b, int& h, int& j) {
-                int qb;
-                const int it = t / J;
-                j = t - it * J;
-                item_coords(it, b, h, qb);
+            // ONE in-order request stream with blocking waits: Q of item `it` (slot it & 1, free once item it - 2 has been
+            // stored), then per 64-key block the K tile of block t and the V tile of block t - 1 — K runs one block ahead
+            // because the score MMA of block t is issued before the P.V MMAs of block t - 1. The first form of this loader
+            // polled three streams (Q, K, V) without blocking and rebuilt every block's coordinates by division: ~2250
+            // cycles of this one thread per block (clock64 timeline: three mbarrier.test_wait at ~150 cycles each, four TMA
+            // issues at ~250, the divisions) — as long as the softmax chain it was feeding, so that nothing done to the
+            // softmax warps could show (with the exponentials compiled out the kernel ran only 8 % faster and the score
+            // issuer waited for K). Now: two try_waits (hardware sleep), four TMA issues, no division per block. Being
+            // parked on a Q slot is harmless: the request comes NK blocks ahead of the consumers, the slot frees within ~2.
+            int t = 0;
+            int pb = 0, ph = 0, pj = 0;  // image / head / block of the V tile still to request (block t - 1)
+            auto load_v = [&](int tv, int b, int h, int j) {
+                const int vs = tv % C::NV;
+                mbar_wait(&v_empty[vs], ((tv / C::NV) & 1) ^ 1);
+                WTR(0, 5);
+                mbar_arrive_expect_tx(&v_full[vs], C::KV_BYTES);
+                tma_load_5d(sV + vs * C::KV_BYTES, &map_kv, &v_full[vs], 0, h, 2, j * KBW, b);
+                if (C::TAIL) tma_load_5d(sV + vs * C::KV_BYTES + C::KV_MAIN, &map_kvt, &v_full[vs], 64, h, 2, j * KBW, b);
             };
-            while (tq < n_local || tk < T || uv < T) {
-                bool progress = false;
-                // Q of item tq: as soon as its slot is free (two slots: at most one item ahead of the one being computed)
-                if (tq < n_local && mbar_test(&q_empty[tq & 1], ((tq >> 1) & 1) ^ 1)) {
-                    int b, h, qb;
-                    item_coords(tq, b, h, qb);
-                    const int qs = tq & 1;
-                    WTR(0, 1);
-                    mbar_arrive_expect_tx(&q_full[qs], C::Q_BYTES + (p.lone ? 2 * DH * 2 : 0));
-                    tma_load_5d(sQ + qs * C::Q_BYTES, &map_q, &q_full[qs], 0, h, 0, qb * QB, b);
-                    if (C::TAIL) tma_load_5d(sQ + qs * C::Q_BYTES + C::Q_MAIN, &map_qt, &q_full[qs], 64, h, 0, qb * QB, b);
-                    if (p.lone) {  // the last token's k and v rows of this head, for the CUDA-core fold-in
-                        const uint8_t* rowp = qkv8 + (static_cast<size_t>(b) * p.S + p.S - 1) * row_bytes + static_cast<size_t>(h) * DH * 2;
-                        bulk_load_1d(sLone + qs * 512, rowp + static_cast<size_t>(p.D) * 2, DH * 2, &q_full[qs]);
-                        bulk_load_1d(sLone + qs * 512 + 256, rowp + static_cast<size_t>(2 * p.D) * 2, DH * 2, &q_full[qs]);
-                    }
-                    ++tq;
-                    progress = true;
+            for (int it = 0; it < n_local; ++it) {
+                int b, h, qb;
+                item_coords(it, b, h, qb);
+                const int qs = it & 1;
+                mbar_wait(&q_empty[qs], ((it >> 1) & 1) ^ 1);
+                WTR(0, 1);
+                mbar_arrive_expect_tx(&q_full[qs], C::Q_BYTES + (p.lone ? 2 * DH * 2 : 0));
+                tma_load_5d(sQ + qs * C::Q_BYTES, &map_q, &q_full[qs], 0, h, 0, qb * QB, b);
+                if (C::TAIL) tma_load_5d(sQ + qs * C::Q_BYTES + C::Q_MAIN, &map_qt, &q_full[qs], 64, h, 0, qb * QB, b);
+                if (p.lone) {  // the last token's k and v rows of this head, for the CUDA-core fold-in
+                    const uint8_t* rowp = qkv8 + (static_cast<size_t>(b) * p.S + p.S - 1) * row_bytes + static_cast<size_t>(h) * DH * 2;
+                    bulk_load_1d(sLone + qs * 512, rowp + static_cast<size_t>(p.D) * 2, DH * 2, &q_full[qs]);
+                    bulk_load_1d(sLone + qs * 512 + 256, rowp + static_cast<size_t>(2 * p.D) * 2, DH * 2, &q_full[qs]);
                 }
-                if (tk < T && mbar_test(&k_empty[tk % C::NK], ((tk / C::NK) & 1) ^ 1)) {
-                    int b, h, j;
-                    coords_of_block(tk, b, h, j);
-                    const int ks = tk % C::NK;
+                for (int j = 0; j < J; ++j, ++t) {
+                    const int ks = t % C::NK;
+                    mbar_wait(&k_empty[ks], ((t / C::NK) & 1) ^ 1);
                     WTR(0, 3);
                     mbar_arrive_expect_tx(&k_full[ks], C::KV_BYTES);
                     tma_load_5d(sK + ks * C::KV_BYTES, &map_kv, &k_full[ks], 0, h, 1, j * KBW, b);
                     if (C::TAIL) tma_load_5d(sK + ks * C::KV_BYTES + C::KV_MAIN, &map_kvt, &k_full[ks], 64, h, 1, j * KBW, b);
-                    ++tk;
-                    progress = true;
+                    if (t > 0) load_v(t - 1, pb, ph, pj);
+                    pb = b, ph = h, pj = j;
                 }
-                if (uv < T && mbar_test(&v_empty[uv % C::NV], ((uv / C::NV) & 1) ^ 1)) {
-                    int b, h, j;
-                    coords_of_block(uv, b, h, j);
-                    const int vs = uv % C::NV;
-                    WTR(0, 5);
-                    mbar_arrive_expect_tx(&v_full[vs], C::KV_BYTES);
-                    tma_load_5d(sV + vs * C::KV_BYTES, &map_kv, &v_full[vs], 0, h, 2, j * KBW, b);
-                    if (C::TAIL) tma_load_5d(sV + vs * C::KV_BYTES + C::KV_MAIN, &map_kvt, &v_full[vs], 64, h, 2, j * KBW, b);
-                    ++uv;
-                    progress = true;
-                }
-                if (!progress) __nanosleep(32);
             }
+            if (t > 0) load_v(t - 1, pb, ph, pj);
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------------------------------ score issuer
@@ -341,14 +349,14 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 WTR(1, 1);
                 mbar_wait(&q_full[qs], (it >> 1) & 1);
                 for (int j = 0; j < J; ++j, ++t) {
-                    const int ks = t % C::NK, sb = t & 1;
+                    const int ks = t % C::NK;
                     WTR(1, 2);
                     mbar_wait(&k_full[ks], (t / C::NK) & 1);
                     WTR(1, 3);
-                    mbar_wait(&s_empty[sb], ((t >> 1) & 1) ^ 1);  // P.V of block t - 2 has read P out of this buffer
+                    mbar_wait(s_free, (t & 1) ^ 1);  // the softmax warps have taken block t - 1 out of the score buffer
                     WTR(1, 4);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + tm_s(sb);
+                    const uint32_t d = tmem_base + TM_S;
                     const uint32_t k_u32 = smem_u32(sK) + ks * C::KV_BYTES;
                     const uint64_t ad = umma_desc_sw128(q_u32);
                     const uint64_t bd = umma_desc_sw128(k_u32);
@@ -361,7 +369,7 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
                         for (int s = 0; s < C::TAIL / 16; ++s) umma_bf16_ss(d, at + 2 * s, bt + 2 * s, idesc, 1u);
                     }
-                    umma_commit(&s_full[sb]);
+                    umma_commit(s_full);
                     umma_commit(&k_empty[ks]);
                     if (j == J - 1) umma_commit(&q_empty[qs]);
                     WTR(1, 5);
@@ -396,7 +404,7 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     const uint32_t b0 = smem_u32(sV) + vs * C::KV_BYTES + (tail_role ? C::KV_MAIN : 0);
                     const int steps = kcols >> 4;  // 16 keys per K-step
                     auto step = [&](int s) {
-                        const uint32_t a = tmem_base + tm_s(sb) + static_cast<uint32_t>(s * 8);
+                        const uint32_t a = tmem_base + tm_p(sb) + static_cast<uint32_t>(s * 8);
                         // V main tile: token-major rows of 128 B = MN-major SWIZZLE_128B operand, 8-key groups 1024 B apart,
                         // one K-step (16 keys) = 2048 B; tail tile: rows of TAIL_ROW bytes in its own swizzle
                         const uint64_t bd = tail_role ? umma_desc(b0 + s * 16 * C::TAIL_ROW, 16, 8 * C::TAIL_ROW, C::TAIL_LAYOUT)
@@ -412,7 +420,7 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     }
                     WTR(3, 6);
                     umma_commit(&v_empty[vs]);
-                    umma_commit(&s_empty[sb]);
+                    umma_commit(&p_empty[sb]);
                     if (j == J - 1) umma_commit(o_full);
                     WTR(3, 7);
                 }
@@ -432,6 +440,12 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #ifdef VLMFW_ATT_TRACE
         int tr_n = (warp == 4 && lane == 0) ? 0 : 8192;
 #endif
+        // Software pipeline over the CTA's key blocks (across item boundaries): the scores of block t + 1 are requested from
+        // TMEM as soon as block t's P has been handed to the tensor memory store, so the load's latency runs under the
+        // store's completion, the p_full hand-off and the loop turn instead of in front of the next block's arithmetic.
+        const int T = n_local * J;
+        uint32_t v[KBW];
+        bool have = false;  // v holds (an in-flight load of) block t's scores
         for (int it = 0; it < n_local; ++it) {
             int b, h, qb;
             item_coords(it, b, h, qb);
@@ -439,20 +453,32 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             // warps whose 32 rows all lie past the last token (ragged last query block: EVA 257, CLIP 577) keep the
             // barrier protocol but skip the TMEM reads and the arithmetic
             const bool warp_live = qb * QB + quarter * 32 < p.S;
+            bool next_item_live = false;
+            if (it + 1 < n_local) {
+                int b2, h2, qb2;
+                item_coords(it + 1, b2, h2, qb2);
+                next_item_live = qb2 * QB + quarter * 32 < p.S;
+            }
             float sL = -INFINITY, pL = 0.f;  // lone last key: its score comes from the epilogue warpgroup
             float m = 0.f, l = 0.f;
             for (int j = 0; j < J; ++j, ++t) {
                 const int valid = p.s_eff - j * KBW;
-                const int sb = t & 1;
-                const uint32_t s_addr = lane_base + tm_s(sb);
+                const int pb = t & 1;
+                const uint32_t s_addr = lane_base + TM_S;
                 WTR(2, 1);
-                mbar_wait(&s_full[sb], (t >> 1) & 1);
+                if (!have) {
+                    mbar_wait(s_full, t & 1);
+                    tc_fence_after();
+                    if (warp_live) tmem_ld_32x64(s_addr, v);
+                }
                 WTR(2, 2);
-                tc_fence_after();
+                tmem_ld_wait();
+                // the block is in registers: the score buffer goes back to the issuer (block t + 1's MMA may overwrite it)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_free);
+                uint32_t w[KBW / 2];
                 if (warp_live) {
-                    uint32_t v[KBW];
-                    tmem_ld_32x64(s_addr, v);
-                    tmem_ld_wait();
                     if (valid < KBW) {
 #pragma unroll
                         for (int i = 0; i < KBW; ++i)
@@ -485,9 +511,9 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         need = true;
                     }
                     if (j > 0 && __any_sync(0xffffffffu, need)) {
-                        // O must hold every P.V up to block t - 1 before it is rescaled: that block's MMAs signal the
-                        // "buffer free" barrier of the OTHER score buffer when they retire
-                        mbar_wait(&s_empty[sb ^ 1], ((t - 1) >> 1) & 1);
+                        // O must hold every P.V up to block t - 1 before it is rescaled: that block's MMAs signal its P
+                        // buffer's "empty" barrier when they retire (and the MMAs of one issuer retire in order)
+                        mbar_wait(&p_empty[pb ^ 1], ((t - 1) >> 1) & 1);
                         tc_fence_after();
 #pragma unroll 1
                         for (int c = 0; c < C::DHP / 16; ++c) {
@@ -502,10 +528,9 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         l *= factor;
                         pL *= factor;
                     }
-                    // exponentials, row sum, P back into TMEM over the first 32 of the 64 score columns just consumed
+                    // exponentials, row sum, P as packed 16-bit pairs
                     const float neg_m = -m;
                     float sum[4] = {0.f, 0.f, 0.f, 0.f};
-                    uint32_t w[KBW / 2];
 #pragma unroll
                     for (int g = 0; g < KBW / 8; ++g) {
                         // 8 independent FFMA, then 8 independent MUFU.EX2 (the chain FFMA -> EX2 -> FADD must not serialise)
@@ -520,24 +545,33 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                             w[g * 4 + i] = WB_PACK(__uint_as_float(v[g * 8 + 2 * i]), __uint_as_float(v[g * 8 + 2 * i + 1]));
                     }
                     l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
-                    WTR(2, 4);
-                    tmem_st_32x32(s_addr, w);
-                    tmem_st_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&p_full[sb]);
-                    WTR(2, 5);
                 } else {
                     // dead warp: its lanes of P must still be defined (they feed MMA rows whose output is never stored)
-                    uint32_t z[KBW / 2];
 #pragma unroll
-                    for (int i = 0; i < KBW / 2; ++i) z[i] = 0u;
-                    tmem_st_32x32(s_addr, z);
-                    tmem_st_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&p_full[sb]);
+                    for (int i = 0; i < KBW / 2; ++i) w[i] = 0u;
                 }
+                WTR(2, 4);
+                // P.V of block t - 2 has read this P buffer
+                mbar_wait(&p_empty[pb], ((t >> 1) & 1) ^ 1);
+                tc_fence_after();
+                tmem_st_32x32(lane_base + tm_p(pb), w);
+                // block t + 1: if its scores are already there (the usual case), start the load now
+                have = false;
+                if (t + 1 < T) {
+                    have = __all_sync(0xffffffffu, mbar_test(s_full, (t + 1) & 1));
+                    if (have) {
+                        tc_fence_after();
+                        if (j + 1 < J ? warp_live : next_item_live) tmem_ld_32x64(s_addr, v);
+                        WTR(2, 6);
+                    } else {
+                        WTR(2, 7);
+                    }
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[pb]);
+                WTR(2, 5);
             }
             // hand (l, p_L) to the epilogue warpgroup and move on to the next item
             sStat[qs * QB + row] = make_float2(l, pL);

@@ -65,6 +65,65 @@ __global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ pi
     }
 }
 
+// uint8 NHWC input, one CTA per (image, patch row): the strip of `patch` image rows (patch * img * 3 contiguous bytes) is
+// staged in shared memory with 16-byte loads, a table maps every k = c p^2 + ky p + kx to its byte offset inside the strip
+// (built once per CTA: the per-element divisions of the generic kernel are gone), and a thread then produces 8 consecutive
+// k of one patch from shared-memory bytes and stores 16 bytes; consecutive threads write consecutive chunks of an output
+// row. The generic kernel above reads single bytes from global memory with three integer divisions per element:
+// 149 us per 256 SigLIP images (0.5 TB/s) against the ~25 us the 116 MB moved here cost at the HBM rate.
+template <bool OUT_F16>
+__global__ void __launch_bounds__(256) im2col_u8_strip_kernel(const uint8_t* __restrict__ pixels, int img, int patch,
+                                                              PixNorm nrm, uint16_t* __restrict__ out, int kpad) {
+    extern __shared__ __align__(16) uint8_t strip_smem[];
+    const int grid_side = img / patch;
+    const int kreal = 3 * patch * patch;
+    const int row_bytes = img * 3;
+    const int strip_bytes = patch * row_bytes;            // a multiple of 16 (checked by the launcher)
+    uint16_t* tab = reinterpret_cast<uint16_t*>(strip_smem + strip_bytes);  // [kpad]: offset of k inside the strip for px = 0
+    const int b = blockIdx.x / grid_side, py = blockIdx.x % grid_side;
+    const uint4* src = reinterpret_cast<const uint4*>(pixels + (static_cast<size_t>(b) * img + static_cast<size_t>(py) * patch) * row_bytes);
+    uint4* dst4 = reinterpret_cast<uint4*>(strip_smem);
+    for (int i = threadIdx.x; i < strip_bytes / 16; i += blockDim.x) dst4[i] = __ldg(src + i);
+    for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
+        int off = 0xFFFF;  // padding column: zero
+        if (k < kreal) {
+            const int c = k / (patch * patch);
+            const int rem = k - c * patch * patch;
+            const int ky = rem / patch, kx = rem - ky * patch;
+            off = ky * row_bytes + kx * 3 + c;
+        }
+        tab[k] = static_cast<uint16_t>(off);
+    }
+    __syncthreads();
+    const int groups = kpad >> 3;
+    const size_t row0 = (static_cast<size_t>(b) * grid_side + py) * grid_side;  // first patch of this strip
+    for (int idx = threadIdx.x; idx < grid_side * groups; idx += blockDim.x) {
+        const int px = idx / groups, g = idx - px * groups;
+        const int base = px * patch * 3;
+        const uint4 t4 = *reinterpret_cast<const uint4*>(tab + g * 8);
+        const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t off = (tw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+            // the channel of k = g * 8 + j is (offset % 3) because every other term of the offset is a multiple of 3
+            float val = 0.f;
+            if (off != 0xFFFFu) {
+                const uint32_t c = off % 3u;
+                // same op order as the HF processor: rescale (x * 1/255) then normalize ((x - mean) / std)
+                val = static_cast<float>(strip_smem[base + off]) * nrm.scale[c] + nrm.shift[c];
+            }
+            f[j] = val;
+        }
+        uint4 o;
+        o.x = pack_16x2<OUT_F16>(f[0], f[1]);
+        o.y = pack_16x2<OUT_F16>(f[2], f[3]);
+        o.z = pack_16x2<OUT_F16>(f[4], f[5]);
+        o.w = pack_16x2<OUT_F16>(f[6], f[7]);
+        *reinterpret_cast<uint4*>(out + (row0 + px) * kpad + g * 8) = o;
+    }
+}
+
 __global__ void fill_cls_kernel(const float* __restrict__ cls_pos0, float* __restrict__ h, int batch, int tokens,
                                 int dim) {
     const int b = blockIdx.x;
@@ -137,6 +196,18 @@ int launch_im2col(const void* pixels, int pix_fmt, int batch, int image_size, in
     const int threads = 256;
     const int grid = grid_for(total, threads);
     uint16_t* o = static_cast<uint16_t*>(out);
+    // uint8 input whose patch-row strip (+ the k table) fits the default 48 KB of shared memory and keeps 16-byte alignment
+    // (all three towers: 14 x 672 B, 14 x 1008 B): strip kernel; anything else: the generic gather
+    const size_t strip_bytes = static_cast<size_t>(patch) * image_size * 3;
+    const size_t strip_smem = strip_bytes + static_cast<size_t>(kpad) * 2;
+    if (pix_fmt == VLMFW_PIX_U8_NHWC && strip_bytes % 16 == 0 && strip_bytes < 0xFFFF && strip_smem <= 48 * 1024 &&
+        (reinterpret_cast<uintptr_t>(pixels) & 15) == 0 && (static_cast<size_t>(image_size) * image_size * 3) % 16 == 0) {
+        const int sgrid = batch * g;
+        if (out_f16) im2col_u8_strip_kernel<true><<<sgrid, threads, strip_smem, stream>>>(static_cast<const uint8_t*>(pixels), image_size, patch, nrm, o, kpad);
+        else im2col_u8_strip_kernel<false><<<sgrid, threads, strip_smem, stream>>>(static_cast<const uint8_t*>(pixels), image_size, patch, nrm, o, kpad);
+        VLMFW_LAUNCH_CHECK();
+        return VLMFW_OK;
+    }
     if (pix_fmt == VLMFW_PIX_U8_NHWC) {
         if (out_f16) im2col_kernel<VLMFW_PIX_U8_NHWC, true><<<grid, threads, 0, stream>>>(pixels, batch, image_size, patch, nrm, o, kpad);
         else im2col_kernel<VLMFW_PIX_U8_NHWC, false><<<grid, threads, 0, stream>>>(pixels, batch, image_size, patch, nrm, o, kpad);

@@ -123,7 +123,25 @@ __device__ __forceinline__ float activation(float x) {
         // x * sigmoid(1.702 x)  (activations.py QuickGELU)
         return __fdividef(x, 1.0f + ex2_approx(x * (-1.702f * 1.4426950408889634f)));
     } else if constexpr (ACT == VLMFW_ACT_GELU_ERF) {
+        // 0.5 x (1 + erf(x / sqrt 2))  (activations.py GELUActivation, EVA / BLIP-2). erf from Abramowitz & Stegun 7.1.26,
+        // erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z), z >= 0 (|error| <= 1.5e-7; the whole expression
+        // stays within 5e-7 of the fp64 GELU, a tenth of the smallest fp16 step it is rounded to): two MUFUs (rcp, ex2) and
+        // twelve FP32 ops without a branch. libdevice's erff cost ~27 instructions per element and made this epilogue, not
+        // the tensor pipe, pace EVA's fc1 (ncu: 63 % tensor-active against 79-83 % for the other two towers' fc1).
+#ifdef VLMFW_ERF_LIBDEVICE  // A/B baseline (tools/ variant builds only)
         return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+#endif
+        const float az = fabsf(x) * 0.70710678118654752f;
+        const float t = rcp_approx(fmaf(az, 0.3275911f, 1.0f));
+        float pl = fmaf(t, 1.061405429f, -1.453152027f);
+        pl = fmaf(pl, t, 1.421413741f);
+        pl = fmaf(pl, t, -0.284496736f);
+        pl = fmaf(pl, t, 0.254829592f);
+        pl *= t;
+        const float e = ex2_approx(az * az * -1.4426950408889634f);
+        const float erf_abs = fmaf(-pl, e, 1.0f);
+        const float hx = 0.5f * x;
+        return fmaf(fabsf(hx), erf_abs, hx);  // x >= 0: hx (1 + erf|z|); x < 0: hx (1 - erf|z|)
     } else {
         return x;
     }
