@@ -217,7 +217,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // The whole warp runs the loop (uniform control flow, every lane waits on the ring barrier); one elected lane
+        // issues. Tile / stage arithmetic and the tensor-map operands then live in uniform registers.
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -231,19 +233,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
                     uint8_t* sb = sa + C::A_BYTES;
-                    if (VLMFW_DBG(p, 1) && (tile != worker || kb >= C::STAGES)) {
-                        if (cta_rank == 0) mbar_arrive(&full_bar[stage]);
-                    } else if constexpr (CG == 2) {
-                        // both CTAs load into their own smem; all bytes are counted on the LEADER's full barrier
-                        const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_tx);
-                        tma_load_2d_pair(sa, &tmap_a, lead_bar, kb * BK, m0);
-                        tma_load_2d_pair(sb, tail ? &tmap_wt : &tmap_w, lead_bar, kb * BK, n0);
-                    } else {
-                        mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
-                        tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * BK, n0);
+                    if (elect_one()) {
+                        if (VLMFW_DBG(p, 1) && (tile != worker || kb >= C::STAGES)) {
+                            if (cta_rank == 0) mbar_arrive(&full_bar[stage]);
+                        } else if constexpr (CG == 2) {
+                            // both CTAs load into their own smem; all bytes are counted on the LEADER's full barrier
+                            const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_tx);
+                            tma_load_2d_pair(sa, &tmap_a, lead_bar, kb * BK, m0);
+                            tma_load_2d_pair(sb, tail ? &tmap_wt : &tmap_w, lead_bar, kb * BK, n0);
+                        } else {
+                            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m0);
+                            tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * BK, n0);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -252,8 +257,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0 && cta_rank == 0) {
+        // ------------------------------------------------------------------ MMA issuer (same form: uniform loop, elected issue)
+        if (cta_rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -270,25 +275,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
                     const uint64_t adesc = umma_desc_sw128(sa);
                     const uint64_t bdesc = umma_desc_sw128(sa + C::A_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                        if (VLMFW_DBG(p, 4)) break;
-                        // advancing K inside the 128B swizzle row: +32 bytes -> +2 in the (addr >> 4) field
-                        if constexpr (CG == 2)
-                            umma_bf16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(ks * 2),
-                                              bdesc + static_cast<uint64_t>(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
-                        else
-                            umma_bf16_ss(d_tmem, adesc + static_cast<uint64_t>(ks * 2),
-                                         bdesc + static_cast<uint64_t>(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
+                        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                            if (VLMFW_DBG(p, 4)) break;
+                            // advancing K inside the 128B swizzle row: +32 bytes -> +2 in the (addr >> 4) field
+                            if constexpr (CG == 2)
+                                umma_bf16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(ks * 2),
+                                                  bdesc + static_cast<uint64_t>(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
+                            else
+                                umma_bf16_ss(d_tmem, adesc + static_cast<uint64_t>(ks * 2),
+                                             bdesc + static_cast<uint64_t>(ks * 2), idesc, (kb | ks) != 0 ? 1u : 0u);
+                        }
+                        // ring slot reusable (in both CTAs of a pair) once these MMAs have read it
+                        if constexpr (CG == 2) {
+                            umma_commit_pair(&empty_bar[stage], 3);
+                            if (kb == num_kb - 1) umma_commit_pair(&tmem_full[acc], 3);
+                        } else {
+                            umma_commit(&empty_bar[stage]);
+                            if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                        }
                     }
-                    // ring slot reusable (in both CTAs of a pair) once these MMAs have read it
-                    if constexpr (CG == 2) {
-                        umma_commit_pair(&empty_bar[stage], 3);
-                        if (kb == num_kb - 1) umma_commit_pair(&tmem_full[acc], 3);
-                    } else {
-                        umma_commit(&empty_bar[stage]);
-                        if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
-                    }
+                    __syncwarp();
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1;

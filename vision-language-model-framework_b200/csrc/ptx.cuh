@@ -225,6 +225,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// One lane of a converged warp (elect.sync). Single-thread roles written as `if (lane == 0) { ... }` put the whole role in
+// divergent code, where ptxas must wrap every uniform-datapath instruction (UTCHMMA, UTMALDG, UTCBAR) in its own
+// ELECT + R2UR.BROADCAST loop; a warp-uniform loop that elects only around the issue keeps descriptors in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
