@@ -287,7 +287,9 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------ TMA loader
         asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");  // warpgroup 0
-        if (lane == 0) {
+        // Like the GEMM's producer: the whole warp runs the loop and waits, one elected lane issues (elect.sync), so the
+        // tensor-map operands and coordinates stay in uniform registers instead of an ELECT + R2UR loop per instruction.
+        {
             const uint8_t* qkv8 = static_cast<const uint8_t*>(p.qkv);
             const size_t row_bytes = static_cast<size_t>(3) * p.D * 2;
             WTR_DECL;
@@ -306,9 +308,12 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 const int vs = tv % C::NV;
                 mbar_wait(&v_empty[vs], ((tv / C::NV) & 1) ^ 1);
                 WTR(0, 5);
-                mbar_arrive_expect_tx(&v_full[vs], C::KV_BYTES);
-                tma_load_5d(sV + vs * C::KV_BYTES, &map_kv, &v_full[vs], 0, h, 2, j * KBW, b);
-                if (C::TAIL) tma_load_5d(sV + vs * C::KV_BYTES + C::KV_MAIN, &map_kvt, &v_full[vs], 64, h, 2, j * KBW, b);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&v_full[vs], C::KV_BYTES);
+                    tma_load_5d(sV + vs * C::KV_BYTES, &map_kv, &v_full[vs], 0, h, 2, j * KBW, b);
+                    if (C::TAIL) tma_load_5d(sV + vs * C::KV_BYTES + C::KV_MAIN, &map_kvt, &v_full[vs], 64, h, 2, j * KBW, b);
+                }
+                __syncwarp();
             };
             for (int it = 0; it < n_local; ++it) {
                 int b, h, qb;
@@ -316,21 +321,27 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 const int qs = it & 1;
                 mbar_wait(&q_empty[qs], ((it >> 1) & 1) ^ 1);
                 WTR(0, 1);
-                mbar_arrive_expect_tx(&q_full[qs], C::Q_BYTES + (p.lone ? 2 * DH * 2 : 0));
-                tma_load_5d(sQ + qs * C::Q_BYTES, &map_q, &q_full[qs], 0, h, 0, qb * QB, b);
-                if (C::TAIL) tma_load_5d(sQ + qs * C::Q_BYTES + C::Q_MAIN, &map_qt, &q_full[qs], 64, h, 0, qb * QB, b);
-                if (p.lone) {  // the last token's k and v rows of this head, for the CUDA-core fold-in
-                    const uint8_t* rowp = qkv8 + (static_cast<size_t>(b) * p.S + p.S - 1) * row_bytes + static_cast<size_t>(h) * DH * 2;
-                    bulk_load_1d(sLone + qs * 512, rowp + static_cast<size_t>(p.D) * 2, DH * 2, &q_full[qs]);
-                    bulk_load_1d(sLone + qs * 512 + 256, rowp + static_cast<size_t>(2 * p.D) * 2, DH * 2, &q_full[qs]);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&q_full[qs], C::Q_BYTES + (p.lone ? 2 * DH * 2 : 0));
+                    tma_load_5d(sQ + qs * C::Q_BYTES, &map_q, &q_full[qs], 0, h, 0, qb * QB, b);
+                    if (C::TAIL) tma_load_5d(sQ + qs * C::Q_BYTES + C::Q_MAIN, &map_qt, &q_full[qs], 64, h, 0, qb * QB, b);
+                    if (p.lone) {  // the last token's k and v rows of this head, for the CUDA-core fold-in
+                        const uint8_t* rowp = qkv8 + (static_cast<size_t>(b) * p.S + p.S - 1) * row_bytes + static_cast<size_t>(h) * DH * 2;
+                        bulk_load_1d(sLone + qs * 512, rowp + static_cast<size_t>(p.D) * 2, DH * 2, &q_full[qs]);
+                        bulk_load_1d(sLone + qs * 512 + 256, rowp + static_cast<size_t>(2 * p.D) * 2, DH * 2, &q_full[qs]);
+                    }
                 }
+                __syncwarp();
                 for (int j = 0; j < J; ++j, ++t) {
                     const int ks = t % C::NK;
                     mbar_wait(&k_empty[ks], ((t / C::NK) & 1) ^ 1);
                     WTR(0, 3);
-                    mbar_arrive_expect_tx(&k_full[ks], C::KV_BYTES);
-                    tma_load_5d(sK + ks * C::KV_BYTES, &map_kv, &k_full[ks], 0, h, 1, j * KBW, b);
-                    if (C::TAIL) tma_load_5d(sK + ks * C::KV_BYTES + C::KV_MAIN, &map_kvt, &k_full[ks], 64, h, 1, j * KBW, b);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&k_full[ks], C::KV_BYTES);
+                        tma_load_5d(sK + ks * C::KV_BYTES, &map_kv, &k_full[ks], 0, h, 1, j * KBW, b);
+                        if (C::TAIL) tma_load_5d(sK + ks * C::KV_BYTES + C::KV_MAIN, &map_kvt, &k_full[ks], 64, h, 1, j * KBW, b);
+                    }
+                    __syncwarp();
                     if (t > 0) load_v(t - 1, pb, ph, pj);
                     pb = b, ph = h, pj = j;
                 }
@@ -340,7 +351,7 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     } else if (warp == 1) {
         // ------------------------------------------------------------------------------------------ score issuer
         asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");  // warpgroup 0
-        if (lane == 0) {
+        {
             int t = 0;
             WTR_DECL;
             for (int it = 0; it < n_local; ++it) {
@@ -361,17 +372,20 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     const uint64_t ad = umma_desc_sw128(q_u32);
                     const uint64_t bd = umma_desc_sw128(k_u32);
                     const uint32_t idesc = umma_idesc_16(QB, kcols_of(j), F16, F16);
+                    const uint64_t at = umma_desc(q_u32 + C::Q_MAIN, 16, 8 * C::TAIL_ROW, C::TAIL_LAYOUT);
+                    const uint64_t bt = umma_desc(k_u32 + C::KV_MAIN, 16, 8 * C::TAIL_ROW, C::TAIL_LAYOUT);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) umma_bf16_ss(d, ad + 2 * s, bd + 2 * s, idesc, s > 0 ? 1u : 0u);
-                    if (C::TAIL) {
-                        const uint64_t at = umma_desc(q_u32 + C::Q_MAIN, 16, 8 * C::TAIL_ROW, C::TAIL_LAYOUT);
-                        const uint64_t bt = umma_desc(k_u32 + C::KV_MAIN, 16, 8 * C::TAIL_ROW, C::TAIL_LAYOUT);
+                        for (int s = 0; s < 4; ++s) umma_bf16_ss(d, ad + 2 * s, bd + 2 * s, idesc, s > 0 ? 1u : 0u);
+                        if (C::TAIL) {
 #pragma unroll
-                        for (int s = 0; s < C::TAIL / 16; ++s) umma_bf16_ss(d, at + 2 * s, bt + 2 * s, idesc, 1u);
+                            for (int s = 0; s < C::TAIL / 16; ++s) umma_bf16_ss(d, at + 2 * s, bt + 2 * s, idesc, 1u);
+                        }
+                        umma_commit(s_full);
+                        umma_commit(&k_empty[ks]);
+                        if (j == J - 1) umma_commit(&q_empty[qs]);
                     }
-                    umma_commit(s_full);
-                    umma_commit(&k_empty[ks]);
-                    if (j == J - 1) umma_commit(&q_empty[qs]);
+                    __syncwarp();
                     WTR(1, 5);
                 }
             }
@@ -383,7 +397,7 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         // Chunks are consumed in the order the softmax warps produce them: the upper 64 keys first (see there).
         asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");  // warpgroup 0
         const bool tail_role = warp == 3;
-        if (lane == 0 && (!tail_role || C::TAIL)) {
+        if (!tail_role || C::TAIL) {
             const uint32_t idesc = tail_role ? umma_idesc_16_bmn(QB, C::TAIL ? C::TAIL : 16, F16) : umma_idesc_16_bmn(QB, 64, F16);
             const uint32_t d = tmem_base + TM_O + (tail_role ? 64u : 0u);
             int t = 0;
@@ -403,6 +417,7 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     tc_fence_after();
                     const uint32_t b0 = smem_u32(sV) + vs * C::KV_BYTES + (tail_role ? C::KV_MAIN : 0);
                     const int steps = kcols >> 4;  // 16 keys per K-step
+                    const bool issuer = elect_one();
                     auto step = [&](int s) {
                         const uint32_t a = tmem_base + tm_p(sb) + static_cast<uint32_t>(s * 8);
                         // V main tile: token-major rows of 128 B = MN-major SWIZZLE_128B operand, 8-key groups 1024 B apart,
@@ -411,17 +426,19 @@ attention_wb_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                                                       : umma_desc(b0 + s * 2048, 16, 1024, 2);
                         umma_f16_ts(d, a, bd, idesc, (j > 0 || s > 0) ? 1u : 0u);
                     };
-                    if (steps == KBW / 16) {
+                    if (issuer) {
+                        if (steps == KBW / 16) {
 #pragma unroll
-                        for (int s = 0; s < KBW / 16; ++s) step(s);
-                    } else {
+                            for (int s = 0; s < KBW / 16; ++s) step(s);
+                        } else {
 #pragma unroll 1
-                        for (int s = 0; s < steps; ++s) step(s);
+                            for (int s = 0; s < steps; ++s) step(s);
+                        }
+                        umma_commit(&v_empty[vs]);
+                        umma_commit(&p_empty[sb]);
+                        if (j == J - 1) umma_commit(o_full);
                     }
-                    WTR(3, 6);
-                    umma_commit(&v_empty[vs]);
-                    umma_commit(&p_empty[sb]);
-                    if (j == J - 1) umma_commit(o_full);
+                    __syncwarp();
                     WTR(3, 7);
                 }
             }
