@@ -45,7 +45,10 @@ constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int STAGING_PER_WARP = 32 * 128;  // generic epilogue: 32 rows x 32 fp32
 // residual epilogue, per warp: ring of RES_NBUF [32 rows x RES_COLS fp32] TMA boxes (64B-swizzled) + one
 // [32 rows x 32 cols] 16-bit box for the fused cast of the updated residual stream (next GEMM's A operand)
-constexpr int RES_NBUF = 3;
+#ifndef VLMFW_RES_NBUF
+#define VLMFW_RES_NBUF 3
+#endif
+constexpr int RES_NBUF = VLMFW_RES_NBUF;
 constexpr int RES_COLS = 16;
 constexpr int RES_BOX_BYTES = 32 * RES_COLS * 4;
 constexpr int H16_BOX_BYTES = 32 * 32 * 2;
@@ -65,6 +68,7 @@ struct Cfg {
                                                : (EPI == VLMFW_EPI_BIAS_RESID_16 ? RES_NBUF * H16_BOX_BYTES : 2 * 2048));
     static constexpr int STAGING_BYTES = EPI_WARPS * STG_PER_WARP;
     static constexpr int BAR_BYTES = 512;
+    static_assert((2 * 6 + 4 + EPI_WARPS * RES_NBUF) * 8 + 4 <= BAR_BYTES, "barrier block too small for the residual ring");
     static constexpr int RING_MAX = (SMEM_LIMIT - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = RING_MAX > 6 ? 6 : RING_MAX;
     static_assert(STAGES >= 2, "operand ring needs at least two stages");
@@ -120,8 +124,15 @@ __device__ __forceinline__ float activation(float x) {
         const float hx = 0.5f * x;
         return fmaf(hx, tanh_approx(u), hx);
     } else if constexpr (ACT == VLMFW_ACT_QUICK_GELU) {
-        // x * sigmoid(1.702 x)  (activations.py QuickGELU)
+        // x * sigmoid(1.702 x)  (activations.py QuickGELU) = 0.5 x (1 + tanh(0.851 x)): one MUFU (tanh.approx, the accuracy
+        // class of the gelu_pytorch_tanh branch above) and three FP32 ops. The ex2 + rcp form needs two MUFUs per element,
+        // and with K = 1024 the tile's MMAs last only 8192 cycles: ncu had CLIP's fc1 at 87.5 % tensor-active against 97 %
+        // for SigLIP's fc1 with its single-MUFU epilogue.
+#ifdef VLMFW_QUICK_GELU_EX2  // A/B baseline (tools/ variant builds only)
         return __fdividef(x, 1.0f + ex2_approx(x * (-1.702f * 1.4426950408889634f)));
+#endif
+        const float hx = 0.5f * x;
+        return fmaf(hx, tanh_approx(0.851f * x), hx);
     } else if constexpr (ACT == VLMFW_ACT_GELU_ERF) {
         // 0.5 x (1 + erf(x / sqrt 2))  (activations.py GELUActivation, EVA / BLIP-2). erf from Abramowitz & Stegun 7.1.26,
         // erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z), z >= 0 (|error| <= 1.5e-7; the whole expression
@@ -366,12 +377,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 1
                 for (int c = 0; c < CHUNKS; ++c, ++q) {
                     const int nc = n0 + c * 32;
+                    float4 bq[8];  // bias (an L2 round trip each: no L1 left beside 227 KB of shared memory) under the TMEM wait
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias != nullptr && nc + 4 * j < p.n) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 4 * j));
+                    }
                     tmem_ld_wait();
                     float y[32];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias != nullptr && nc + 4 * j < p.n) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 4 * j));
+                        const float4 bv = bq[j];
                         y[4 * j + 0] = fmaf(rstd, __uint_as_float(v[4 * j + 0]), bv.x);
                         y[4 * j + 1] = fmaf(rstd, __uint_as_float(v[4 * j + 1]), bv.y);
                         y[4 * j + 2] = fmaf(rstd, __uint_as_float(v[4 * j + 2]), bv.z);
@@ -461,6 +477,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int c = 0; c < RCHUNKS; ++c, ++q) {
                     if (VLMFW_DBG(p, 2)) continue;
                     const int nc = n0 + c * RC;
+                    // The chunk's 32 bias values first: with the whole L1 carved out as shared memory every __ldg is an L2
+                    // round trip, and inside the update loop below each of the four loads sat behind the previous group's
+                    // st.shared (ncu source view of out-proj: 28 % of all samples on the four FFMAs that consume them —
+                    // 3700 cycles per chunk, so that the K = 1152 GEMM was bound by its epilogue). Issued here they fly
+                    // under the TMEM load and the barrier waits.
+                    float4 bq[RC / 4];
+#pragma unroll
+                    for (int j = 0; j < RC / 4; ++j) {
+                        bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias != nullptr && nc + 4 * j < p.n) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 4 * j));
+                    }
                     uint32_t v[RC];
                     tmem_ld_32x32(lane_taddr + static_cast<uint32_t>(acc * BN + c * RC), v);
                     const uint32_t b = q % RES_NBUF;
@@ -480,13 +507,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
 #pragma unroll
                     for (uint32_t j = 0; j < 4; ++j) {  // 16 bytes = 8 columns
-                        float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        if (p.bias != nullptr && nc + 8 * static_cast<int>(j) < p.n) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 8 * j));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 8 * j + 4));
-                            bv[0] = b0.x, bv[1] = b0.y, bv[2] = b0.z, bv[3] = b0.w;
-                            bv[4] = b1.x, bv[5] = b1.y, bv[6] = b1.z, bv[7] = b1.w;
-                        }
+                        const float4 b0 = bq[2 * j], b1 = bq[2 * j + 1];
+                        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                         const uint32_t a = box + ((j ^ sw) << 4);
                         uint32_t u[4];
                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
@@ -566,6 +588,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int c = 0; c < RCHUNKS; ++c, ++q) {
                     if (VLMFW_DBG(p, 2)) continue;
                     const int nc = n0 + c * RES_COLS;
+                    float4 bq[RES_COLS / 4];  // bias first (see the 16-bit residual epilogue)
+#pragma unroll
+                    for (int j = 0; j < RES_COLS / 4; ++j) {
+                        bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias != nullptr && nc + 4 * j < p.n) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 4 * j));
+                    }
                     uint32_t v[RES_COLS];
                     tmem_ld_row(lane_taddr + static_cast<uint32_t>(acc * BN + c * RES_COLS), v);
                     const uint32_t b = q % RES_NBUF;
@@ -579,9 +607,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     uint32_t hp[RES_COLS / 2];
 #pragma unroll
                     for (uint32_t j = 0; j < RES_COLS / 4; ++j) {
-                        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias != nullptr && nc + 4 * static_cast<int>(j) < p.n)
-                            bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 4 * j));
+                        const float4 bv = bq[j];
                         const uint32_t a = box + ((j ^ sw) << 4);
                         float4 r;
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
