@@ -1,14 +1,27 @@
 set -x
-V=$PWD/tools/_variants
-timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "gemm" --timeout 120 --timeout-method thread 2>&1 | tail -2
-for i in 1 2; do
-for v in main nbuf3; do lib=""; [ $v != main ] && lib=$V/lib_$v.so
-echo "== $v"; VLMFW_B200_LIB=$lib timeout 200 python tools/bench_kernels.py --only siglip --no-cublas 2>&1 | grep kernel | cut -c1-120
-done; done
-for v in main nbuf3; do lib=""; [ $v != main ] && lib=$V/lib_$v.so
-echo "== $v eva/clip"; VLMFW_B200_LIB=$lib timeout 200 python tools/bench_kernels.py --only fc --no-cublas --m 32896 2>&1 | grep -E "clip|eva" | cut -c1-120
+TAG=r2y
+timeout 1500 python -m pytest tests -m gpu -x -q -s --timeout 600 --timeout-method thread > gpurun_out/${TAG}_gpu_tests.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/${TAG}_gpu_tests.log; grep "parity-live" gpurun_out/${TAG}_gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${TAG}_smoke.log
+timeout 400 python bench.py > gpurun_out/${TAG}_bench_siglip_f16.json 2> gpurun_out/${TAG}_bench_siglip_f16.err; echo "bench rc=$?"
+timeout 400 python bench.py --dtype bf16 --no-cpu-baseline > gpurun_out/${TAG}_bench_siglip_bf16.json 2> gpurun_out/${TAG}_bench_siglip_bf16.err; echo "bench bf16 rc=$?"
+for m in clip eva; do timeout 400 python bench.py --model $m --no-cpu-baseline > gpurun_out/${TAG}_bench_$m.json 2> gpurun_out/${TAG}_bench_$m.err; echo "bench $m rc=$?"; done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r2y_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, d.get('value'), d.get('e2e',{}).get('value'), d.get('ms_per_step'), d.get('clocks',{}).get('sm_mhz'), d.get('roofline',{}).get('frac'), d.get('roofline',{}).get('step_frac_burst'))
+    except Exception as e: print(f, 'ERR', e)
+PY
+B="python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline"
+for m in siglip clip eva; do
+VLMFW_PROFILE_RANGE=1 timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_$m.csv $B --model $m > gpurun_out/${TAG}_ncu_launches_$m.log 2>&1; echo "launches $m rc=$?"
 done
-for v in main nbuf3 main nbuf3; do lib=""; [ $v != main ] && lib=$V/lib_$v.so
-VLMFW_B200_LIB=$lib timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2w_bench_$v.json 2> gpurun_out/r2w_bench_$v.err; echo "bench $v rc=$?"
-python -c "import sys,json; d=json.loads(open('gpurun_out/r2w_bench_$v.json').read().strip().splitlines()[-1]); print('siglip $v', d['value'], d['e2e']['value'], d['ms_per_step'], d['clocks']['sm_mhz'], d['roofline']['kernel_ms'], d['roofline']['frac'])"
-done
+full() { name=$1; model=$2; shift 2
+  VLMFW_PROFILE_RANGE=1 timeout 400 ncu --set full --clock-control none --import-source on --profile-from-start off "$@" -o /tmp/$name -f $B --model $model > gpurun_out/${TAG}_ncu_$name.log 2>&1; echo "full $name rc=$?"
+  python tools/ncu_summary.py /tmp/$name.ncu-rep --csv gpurun_out/${TAG}_ncu_$name.csv > /dev/null 2>&1
+  ncu -i /tmp/$name.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_${name}_raw.csv 2>/dev/null
+}
+full layer_siglip siglip --launch-skip 52 --launch-count 5
+full layer_clip clip --launch-skip 55 --launch-count 5
+full layer_eva eva --launch-skip 54 --launch-count 5
