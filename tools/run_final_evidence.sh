@@ -1,3 +1,6 @@
+# Evidence run of one build on one B200 (profiles/r2_y_*): full GPU test suite (-s keeps the live-oracle parity lines), smoke, the bench
+# lines of the three towers (+ bf16), then the ncu launch list of one eager step and --set full of one encoder layer per tower.
+# Reports are summarised ON THE BOX (tools/ncu_summary.py + the raw page as csv): gpurun_out/ brings back at most 64 MiB.
 set -x
 TAG=r2y
 timeout 1500 python -m pytest tests -m gpu -x -q -s --timeout 600 --timeout-method thread > gpurun_out/${TAG}_gpu_tests.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/${TAG}_gpu_tests.log; grep "parity-live" gpurun_out/${TAG}_gpu_tests.log

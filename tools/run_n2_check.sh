@@ -1,3 +1,5 @@
+# 2-GPU check of one build (one box): sharded inference / DP probe training equal the single-process results, headline bench
+# and probe-training bench under torchrun.
 set -x
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node 2"
 timeout 240 $TR --master-port 29521 tools/dp_check.py > gpurun_out/r2y_dp_check_n2.json 2> gpurun_out/r2y_dp_check_n2.err; echo "dp_check rc=$?"; tail -1 gpurun_out/r2y_dp_check_n2.json | cut -c1-600
