@@ -78,12 +78,20 @@ def cpu_model_string() -> str:
 
 
 def library_build_id() -> str:
-    """sha256 (first 12 hex digits) of the shipped libvlmfw_b200.so: ties a profile capture to the build it was taken on."""
+    """sha256 (first 12 hex digits) over the sources libvlmfw_b200.so is built from (csrc/*.cu, *.cuh, build.sh and the
+    C-ABI header, in name order): ties a profile capture to the build it was taken on, and survives a rebuild of the same
+    sources on another machine (the binary itself is not bit-reproducible across checkouts)."""
     from vlmfw_b200 import _lib
 
+    h = hashlib.sha256()
     try:
-        with open(_lib.LIB_PATH, "rb") as f:
-            return hashlib.sha256(f.read()).hexdigest()[:12]
+        names = sorted(f for f in os.listdir(_lib.CSRC_DIR) if f.endswith((".cu", ".cuh", ".sh")))
+        for path in [os.path.join(_lib.CSRC_DIR, f) for f in names] + [os.path.join(ROOT, "include", "vlmfw_b200.h")]:
+            with open(path, "rb") as f:
+                h.update(f.read())
+        if not os.path.exists(_lib.LIB_PATH):
+            return "missing"
+        return h.hexdigest()[:12]
     except OSError:
         return "missing"
 
