@@ -77,15 +77,19 @@ def cpu_model_string() -> str:
     return platform.processor() or platform.machine()
 
 
-def library_build_id() -> str:
+GEMM_SOURCES = ("common.cuh", "gemm_tcgen05.cu", "ptx.cuh", "build.sh")  # what the roofline kernel is compiled from
+
+
+def library_build_id(only=None) -> str:
     """sha256 (first 12 hex digits) over the sources libvlmfw_b200.so is built from (csrc/*.cu, *.cuh, build.sh and the
-    C-ABI header, in name order): ties a profile capture to the build it was taken on, and survives a rebuild of the same
-    sources on another machine (the binary itself is not bit-reproducible across checkouts)."""
+    C-ABI header, in name order; ``only``: a subset of csrc/ names): ties a profile capture to the build it was taken on,
+    and survives a rebuild of the same sources on another machine (the binary itself is not bit-reproducible across
+    checkouts)."""
     from vlmfw_b200 import _lib
 
     h = hashlib.sha256()
     try:
-        names = sorted(f for f in os.listdir(_lib.CSRC_DIR) if f.endswith((".cu", ".cuh", ".sh")))
+        names = sorted(f for f in os.listdir(_lib.CSRC_DIR) if f.endswith((".cu", ".cuh", ".sh")) and (only is None or f in only))
         for path in [os.path.join(_lib.CSRC_DIR, f) for f in names] + [os.path.join(ROOT, "include", "vlmfw_b200.h")]:
             with open(path, "rb") as f:
                 h.update(f.read())
@@ -432,9 +436,10 @@ def run_b200_arm(args):
         key = f"{args.model}_{args.dtype}" if f"{args.model}_{args.dtype}" in rt else args.model
         if key in rt and B == rt[key].get("batch", 256):
             traffic = rt[key]["dram_bytes_read"] + rt[key]["dram_bytes_write"]
-            cap_build = rt[key].get("build_id", rt.get("build_id"))
-            traffic_src = {"capture": rt[key].get("source", rt.get("source")), "captured_on_build": cap_build,
-                           "this_build": build_id, "same_build": cap_build == build_id}
+            # the capture is tied to the sources of the kernel it measured (the GEMM), not to the whole library
+            cap_build, gemm_id = rt[key].get("gemm_sources_id", rt.get("gemm_sources_id")), library_build_id(GEMM_SOURCES)
+            traffic_src = {"capture": rt[key].get("source", rt.get("source")), "captured_on_gemm_sources": cap_build,
+                           "this_gemm_sources": gemm_id, "same_build": cap_build == gemm_id}
     except (OSError, KeyError, ValueError):
         pass
     roofline = {

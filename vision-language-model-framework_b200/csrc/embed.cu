@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(256) im2col_u8_strip_kernel(const uint8_t* __r
     const int kreal = 3 * patch * patch;
     const int row_bytes = img * 3;
     const int strip_bytes = patch * row_bytes;            // a multiple of 16 (checked by the launcher)
-    uint16_t* tab = reinterpret_cast<uint16_t*>(strip_smem + strip_bytes);  // [kpad]: offset of k inside the strip for px = 0
+    // [kpad]: offset of k inside the strip for px = 0 (low 14 bits) | channel << 14 (0xFFFF: padding column)
+    uint16_t* tab = reinterpret_cast<uint16_t*>(strip_smem + strip_bytes);
     const int b = blockIdx.x / grid_side, py = blockIdx.x % grid_side;
     const uint4* src = reinterpret_cast<const uint4*>(pixels + (static_cast<size_t>(b) * img + static_cast<size_t>(py) * patch) * row_bytes);
     uint4* dst4 = reinterpret_cast<uint4*>(strip_smem);
@@ -90,13 +91,17 @@ __global__ void __launch_bounds__(256) im2col_u8_strip_kernel(const uint8_t* __r
             const int c = k / (patch * patch);
             const int rem = k - c * patch * patch;
             const int ky = rem / patch, kx = rem - ky * patch;
-            off = ky * row_bytes + kx * 3 + c;
+            off = (ky * row_bytes + kx * 3 + c) | (c << 14);
         }
         tab[k] = static_cast<uint16_t>(off);
     }
     __syncthreads();
     const int groups = kpad >> 3;
     const size_t row0 = (static_cast<size_t>(b) * grid_side + py) * grid_side;  // first patch of this strip
+    // per-channel constants in registers, picked by selects: indexing the kernel-parameter arrays with a per-lane channel
+    // is a divergent constant load, and those saturated the address-divergence unit (ncu: ADU pipe 97 % busy, 120 us)
+    const float s0 = nrm.scale[0], s1 = nrm.scale[1], s2 = nrm.scale[2];
+    const float h0 = nrm.shift[0], h1 = nrm.shift[1], h2 = nrm.shift[2];
     for (int idx = threadIdx.x; idx < grid_side * groups; idx += blockDim.x) {
         const int px = idx / groups, g = idx - px * groups;
         const int base = px * patch * 3;
@@ -105,13 +110,13 @@ __global__ void __launch_bounds__(256) im2col_u8_strip_kernel(const uint8_t* __r
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const uint32_t off = (tw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-            // the channel of k = g * 8 + j is (offset % 3) because every other term of the offset is a multiple of 3
+            const uint32_t e = (tw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
             float val = 0.f;
-            if (off != 0xFFFFu) {
-                const uint32_t c = off % 3u;
+            if (e != 0xFFFFu) {
+                const uint32_t c = e >> 14, off = e & 0x3FFFu;
+                const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2), sh = c == 0 ? h0 : (c == 1 ? h1 : h2);
                 // same op order as the HF processor: rescale (x * 1/255) then normalize ((x - mean) / std)
-                val = static_cast<float>(strip_smem[base + off]) * nrm.scale[c] + nrm.shift[c];
+                val = static_cast<float>(strip_smem[base + off]) * sc + sh;
             }
             f[j] = val;
         }
@@ -200,7 +205,7 @@ int launch_im2col(const void* pixels, int pix_fmt, int batch, int image_size, in
     // (all three towers: 14 x 672 B, 14 x 1008 B): strip kernel; anything else: the generic gather
     const size_t strip_bytes = static_cast<size_t>(patch) * image_size * 3;
     const size_t strip_smem = strip_bytes + static_cast<size_t>(kpad) * 2;
-    if (pix_fmt == VLMFW_PIX_U8_NHWC && strip_bytes % 16 == 0 && strip_bytes < 0xFFFF && strip_smem <= 48 * 1024 &&
+    if (pix_fmt == VLMFW_PIX_U8_NHWC && strip_bytes % 16 == 0 && strip_bytes < 0x4000 && strip_smem <= 48 * 1024 &&
         (reinterpret_cast<uintptr_t>(pixels) & 15) == 0 && (static_cast<size_t>(image_size) * image_size * 3) % 16 == 0) {
         const int sgrid = batch * g;
         if (out_f16) im2col_u8_strip_kernel<true><<<sgrid, threads, strip_smem, stream>>>(static_cast<const uint8_t*>(pixels), image_size, patch, nrm, o, kpad);
