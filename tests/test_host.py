@@ -156,20 +156,39 @@ def test_sass_of_the_hot_kernels_is_tcgen05_and_tma():
     so = os.path.join(os.path.dirname(_lib.__file__), "libvlmfw_b200.so")
     out = subprocess.run([tool, "-sass", so], capture_output=True, text=True, timeout=300).stdout
     assert "sm_100a" in out or "EF_CUDA_SM100" in out, "no sm_100a code object in the library"
-    per_fn = {}
+    per_fn, per_fn_seq = {}, {}
     name = None
     for line in out.splitlines():
         m = re.match(r"\s*Function : (\S+)", line)
         if m:
             name = m.group(1)
-            per_fn[name] = set()
+            per_fn[name], per_fn_seq[name] = set(), []
         elif name is not None:
             m = re.match(r"\s*/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
             if m:
                 per_fn[name].add(m.group(1))
+                per_fn_seq[name].append(m.group(1))
     gemms = {f: ops for f, ops in per_fn.items() if "gemm_bf16_tn_kernel" in f}
-    atts = {f: ops for f, ops in per_fn.items() if "attention_tc_kernel" in f}
-    assert len(gemms) >= 6 and len(atts) >= 2, (len(gemms), len(atts))
+    atts = {f: ops for f, ops in per_fn.items() if "attention_tc_kernel" in f or "attention_wb_kernel" in f}
+    wbs = {f: ops for f, ops in per_fn.items() if "attention_wb_kernel" in f}
+    assert len(gemms) >= 6 and len(atts) >= 8 and len(wbs) == 6, (len(gemms), len(atts), len(wbs))
+    for f, ops in wbs.items():  # the three towers' attention: P written to and read from tensor memory
+        assert "STTM" in ops, f"{f}: probabilities not stored to TMEM"
+    # Single-thread roles (TMA producer, MMA issuer) are warp-uniform loops with elect.sync around the issue: in divergent
+    # `if (lane == 0)` code ptxas wraps every UTCHMMA / UTMALDG / UTCBAR in its own ELECT + R2UR.BROADCAST loop, which cost
+    # the GEMMs 15-20 % of their tensor-pipe time. In the elect form the MMAs of a k-block
+    # (four for the GEMMs' 64-wide stage, four or five for a 64-key score block) sit back to back in the instruction stream.
+    def longest_run(seq, op):
+        best = cur = 0
+        for o in seq:
+            cur = cur + 1 if o == op else 0
+            best = max(best, cur)
+        return best
+
+    for f in list(wbs) + list(gemms):
+        assert "ELECT" in per_fn[f], f"{f}: no elect.sync"
+        need = 4 if f in gemms else 2  # attention: ptxas weaves the tail tile's descriptor arithmetic between the MMAs
+        assert longest_run(per_fn_seq[f], "UTCHMMA") >= need, f"{f}: tcgen05.mma issued one per ELECT / R2UR loop"
     for f, ops in {**gemms, **atts}.items():
         assert "UTCHMMA" in ops, f"{f}: no tcgen05.mma"
         assert "UTMALDG" in ops, f"{f}: operands not loaded by TMA"
